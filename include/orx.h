@@ -1,0 +1,126 @@
+/* orx -- B200-native exact cosine top-k retrieval engine: the C-ABI boundary.
+ *
+ * The reference (Molyleaf/Outline-RAG) has no FFI; its seam for this path is the
+ * LangChain VectorStore object bound to `rag.vector_store`
+ * (reference app/rag.py:28, created at app/rag.py:69-79).  Every entry point below
+ * names the reference call it stands in for; INTEGRATION.md shows the ctypes
+ * binding and the drop-in class that replaces `AsyncPGVectorStore` at rag.py:69.
+ *
+ * Conventions: return 0 = OK, negative = error (message via orx_last_error(),
+ * thread-local).  The caller owns every buffer it passes; the library owns all
+ * device memory.  Pointer arguments documented "host or device" are classified
+ * with cudaPointerGetAttributes.  One orx_index lives on ONE GPU (one process per
+ * GPU; row-sharding across GPUs is done above this API with torch.distributed,
+ * see outline_rag_b200/sharded.py).  Calls on one index are serialised
+ * internally (stream order = call order, so a search issued after an upsert sees
+ * it: at least as consistent as the reference's separate delete / insert
+ * transactions, app/rag.py:231-235).
+ */
+#ifndef ORX_H
+#define ORX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORX_DIM 1024            /* VECTOR_DIM, reference app/config.py:8 */
+#define ORX_MAX_K 32            /* TOP_K is 12, reference app/config.py:253 */
+
+#define ORX_DTYPE_F32 0         /* rows stored verbatim (fp32) + per-row 1/norm   */
+#define ORX_DTYPE_BF16 1        /* rows stored as RNE-bf16 of the normalised row  */
+
+#define ORX_OK 0
+#define ORX_ERR_INVALID (-1)    /* bad argument (k, nq, null pointer, ...)        */
+#define ORX_ERR_DIM (-2)        /* "expected 1024 dimensions" (pgvector CheckDim) */
+#define ORX_ERR_NONFINITE (-3)  /* "NaN/infinite value not allowed in vector"     */
+#define ORX_ERR_CUDA (-4)       /* CUDA runtime error / out of device memory      */
+#define ORX_ERR_CAPACITY (-5)   /* table cannot grow further                      */
+
+typedef struct orx_index orx_index;
+
+/* 128-bit chunk id = `langchain_id UUID` (reference app/database.py:119).
+ * Ordered as the big-endian integer (hi, lo): the order Postgres gives uuid and
+ * the tie-break of this build's ordering contract (distance ASC, id ASC). */
+typedef struct orx_id { uint64_t hi, lo; } orx_id;
+
+/* Counters for bench.py / tests (cumulative since create unless noted). */
+typedef struct orx_stats {
+    uint64_t kernel_launches;     /* kernels this library launched                */
+    uint64_t searches;            /* orx_search* calls                             */
+    uint64_t queries;             /* queries answered                              */
+    uint64_t fallback_gemv;       /* queries re-run on the fp32 scan (coarse pass unproven) */
+    uint64_t fallback_exhaustive; /* queries answered by the threshold-collect pass */
+    uint64_t rows_moved;          /* rows relocated by delete compaction           */
+    float    last_scan_ms;        /* device time of the last search's scan kernel(s) */
+    float    last_search_ms;      /* device time of the last search, first to last kernel */
+    int      last_path;           /* 0 none, 1 gemv scan, 2 tcgen05 scan           */
+    int      reserved;
+} orx_stats;
+
+/* Replaces `AsyncPGVectorStore.create(engine, embedding_service,
+ * table_name="langchain_pg_embedding", ...)` (reference app/rag.py:69-79) and the
+ * DDL `embedding vector(1024)` (app/database.py:118-131).  dim must be ORX_DIM. */
+int orx_create(orx_index **out, int dim, int dtype, uint64_t capacity_rows, int device);
+void orx_destroy(orx_index *idx);
+
+/* Kernels are launched on this CUDA stream (a cudaStream_t; NULL = legacy default
+ * stream).  Python hands over torch's current stream so torch.cuda.Event sees them. */
+int orx_set_stream(orx_index *idx, void *cuda_stream);
+
+uint64_t orx_size(const orx_index *idx);       /* live rows */
+uint64_t orx_capacity(const orx_index *idx);
+int orx_dtype(const orx_index *idx);
+int orx_get_stats(const orx_index *idx, orx_stats *out);
+
+/* Replaces `vector_store.aadd_documents(chunks)` -> per-row
+ * `INSERT ... ON CONFLICT (langchain_id) DO UPDATE` (reference app/rag.py:235).
+ * ids [n]; vecs [n, dim] fp32, host or device.  An id already present is replaced
+ * in place; an id repeated inside the batch keeps its last occurrence.  The whole
+ * batch is rejected (table unchanged) on a NaN/Inf element (ORX_ERR_NONFINITE). */
+int orx_upsert(orx_index *idx, const orx_id *ids, const float *vecs, uint64_t n, int dim);
+
+/* Replaces `vector_store.adelete(ids=[...])` -> `DELETE ... WHERE langchain_id IN (...)`
+ * (reference app/rag.py:231, :371).  Unknown ids are ignored, like the SQL. */
+int orx_delete(orx_index *idx, const orx_id *ids, uint64_t n, uint64_t *n_removed);
+
+/* 1 if the id is live, 0 if not. */
+int orx_contains(const orx_index *idx, orx_id id);
+
+/* Replaces the SQL of `asimilarity_search_with_score_by_vector(embedding, k)`:
+ *   SELECT ..., cosine_distance("embedding", :q) AS distance
+ *   FROM langchain_pg_embedding ORDER BY "embedding" <=> :q LIMIT :k
+ * (langchain-postgres 0.0.16 [UPSTREAM]; reached from reference app/rag.py:85-87,
+ * called at app/blueprints/api.py:122) with EXACT sequential-scan semantics.
+ * queries [nq, dim] fp32, host or device.  Outputs (host or device, same kind for
+ * all three): out_ids [nq, k], out_dist [nq, k] = cosine distance as float8,
+ * out_counts [nq] = min(k, live rows).  Order: distance ASC, NaN last, id ASC.
+ * Unused tail slots are filled with id (0,0) / NaN. */
+int orx_search(orx_index *idx, const float *queries, int nq, int dim, int k,
+               orx_id *out_ids, double *out_dist, int *out_counts);
+
+/* Merge `n_lists` per-shard results (each [nq, k] as written by orx_search, all on
+ * this index's device or all on the host) into the global top-k with the same
+ * ordering.  The on-device step after the NCCL allgather of the row-sharded path. */
+int orx_merge_topk(orx_index *idx, int n_lists, int nq, int k,
+                   const orx_id *ids, const double *dist, const int *counts,
+                   orx_id *out_ids, double *out_dist, int *out_counts);
+
+/* Read back stored rows (as fp32) by id -- snapshot / debugging / tests.
+ * out_vecs [n, dim] host; out_found [n] host (1/0). */
+int orx_fetch(orx_index *idx, const orx_id *ids, uint64_t n, float *out_vecs, int *out_found);
+
+/* Synthetic bge-m3-shaped table generator, bit-identical to
+ * outline_rag_b200/synth.py.  Fills dst_device [n_rows, 1024] fp32 with rows
+ * row_start .. row_start+n_rows-1.  centres/mean are built on first use. */
+int orx_synth_rows(int device, void *cuda_stream, uint64_t seed, uint32_t n_centres,
+                   uint64_t row_start, uint64_t n_rows, float *dst_device);
+
+const char *orx_last_error(void);
+const char *orx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORX_H */

@@ -1,0 +1,393 @@
+// Query preparation, candidate finalisation (merge + canonical rescore + ordering + proof),
+// shard merge, and the exhaustive threshold-collect fallback.
+//
+// The rescore is what makes the answer bit-exact and independent of scan order: every
+// candidate's cosine distance is recomputed in binary64 in the fixed halving-tree order of
+// oracle/cosine_topk.py:canon_distance, then candidates are ordered by the SQL contract
+// (distance ASC, NaN last, id ASC) of `ORDER BY embedding <=> :q LIMIT :k`
+// (reference app/rag.py:85-87 -> langchain-postgres [UPSTREAM]).
+#include "scan_common.cuh"
+#include "internal.h"
+
+namespace orx {
+
+// --------------------------------------------------------------- prep_queries
+// One warp per query: pgvector's input check (NaN/Inf -> error), canonical |q|^2,
+// normalised fp32 copy qhat (and its RNE bf16 image for the tcgen05 bf16 scan).
+__global__ void __launch_bounds__(128)
+prep_queries_kernel(const float *__restrict__ q_all, int nq, float *__restrict__ qhat_all,
+                    __nv_bfloat16 *__restrict__ qhat16_all, QueryPrep *__restrict__ prep) {
+    const int lane = threadIdx.x & 31;
+    const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (qi >= nq) return;
+    const float *q = q_all + (size_t)qi * ORX_DIM;
+    float x[32];
+    double p[32];
+    bool bad = false;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        x[j] = q[lane + 32 * j];
+        bad |= !isfinite(x[j]);
+        p[j] = __dmul_rn((double)x[j], (double)x[j]);
+    }
+    const double n2q = bcast_lane0(canon_tree_1024(p));
+    const bool any_bad = __any_sync(FULL_MASK, bad);
+    const bool zero = !(n2q > 0.0);
+    const double inv = (any_bad || zero) ? 0.0 : __ddiv_rn(1.0, __dsqrt_rn(n2q));
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float h = (any_bad || zero) ? 0.f : __double2float_rn(__dmul_rn((double)x[j], inv));
+        qhat_all[(size_t)qi * ORX_DIM + lane + 32 * j] = h;
+        if (qhat16_all) qhat16_all[(size_t)qi * ORX_DIM + lane + 32 * j] = __float2bfloat16_rn(h);
+    }
+    if (lane == 0) {
+        prep[qi].n2q = n2q;
+        prep[qi].nonfinite = any_bad ? 1 : 0;
+        prep[qi].zero = zero ? 1 : 0;
+    }
+}
+
+void launch_prep_queries(const float *q, int nq, float *qhat, void *qhat_bf16, QueryPrep *prep,
+                         cudaStream_t st) {
+    if (nq <= 0) return;
+    prep_queries_kernel<<<(nq + 3) / 4, 128, 0, st>>>(q, nq, qhat,
+                                                      static_cast<__nv_bfloat16 *>(qhat_bf16), prep);
+}
+
+// ------------------------------------------------------------------- finalize
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_WARPS = FIN_THREADS / 32;
+
+template <typename T, int S>
+__global__ void __launch_bounds__(FIN_THREADS)
+finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
+                const orx_id *__restrict__ row_ids, const float *__restrict__ q_all,
+                const QueryPrep *__restrict__ prep, const uint64_t *__restrict__ partial_all,
+                int nparts, int k, uint32_t n_rows, double eps, orx_id *__restrict__ out_ids,
+                double *__restrict__ out_dist, int *__restrict__ out_counts,
+                int *__restrict__ out_flags) {
+    constexpr int K = 32 * S;
+    __shared__ uint64_t s_keys[FIN_WARPS][K];
+    __shared__ uint64_t s_cand[K];
+    __shared__ double s_dist[K];
+    __shared__ uint64_t s_hi[K], s_lo[K];
+    __shared__ double s_kth;
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int qi = blockIdx.x;
+    const uint64_t *partial = partial_all + (size_t)qi * nparts * K;
+    const int total = nparts * K;
+    if (threadIdx.x == 0) s_kth = __longlong_as_double(0x7ff8000000000000ll);
+
+    // 1. fold the per-CTA lists into the query's top-K fast candidates
+    WarpTopK<S> top;
+    top.init();
+    for (int base = warp * 32; base < total; base += FIN_WARPS * 32) {
+        const int i = base + lane;
+        top.offer_lanes(i < total ? partial[i] : 0ull, lane);
+    }
+    top.store(s_keys[warp], lane);
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < FIN_WARPS; ++w) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) top.offer_lanes(s_keys[w][s * 32 + lane], lane);
+        }
+        top.store(s_cand, lane);
+    }
+    __syncthreads();
+
+    // 2. canonical rescore, one warp per candidate
+    const float *q = q_all + (size_t)qi * ORX_DIM;
+    const double n2q = prep[qi].n2q;
+    for (int c = warp; c < K; c += FIN_WARPS) {
+        const uint64_t key = s_cand[c];
+        if (key == 0ull) {                    // empty slot: sorts after everything
+            if (lane == 0) {
+                s_dist[c] = __longlong_as_double(0x7ff8000000000000ll);
+                s_hi[c] = ~0ull;
+                s_lo[c] = ~0ull;
+            }
+            continue;
+        }
+        const uint32_t row = key_row(key);
+        const double dot = warp_canon_dot<T>(table + (size_t)row * ORX_DIM, q, lane);
+        if (lane == 0) {
+            s_dist[c] = canon_dist(dot, n2[row], n2q);
+            s_hi[c] = row_ids[row].hi;
+            s_lo[c] = row_ids[row].lo;
+        }
+    }
+    __syncthreads();
+
+    // 3. order by (distance ASC, NaN last, id ASC): rank by counting
+    const int t = threadIdx.x;
+    int valid = 0;
+    for (int c = 0; c < K; ++c) valid += (s_cand[c] != 0ull);
+    const int count = min(k, valid);
+    if (t < K && s_cand[t] != 0ull) {
+        int rank = 0;
+        const double d = s_dist[t];
+        const uint64_t hi = s_hi[t], lo = s_lo[t];
+        for (int c = 0; c < K; ++c)
+            rank += (c != t && s_cand[c] != 0ull && sorts_before(s_dist[c], s_hi[c], s_lo[c], d, hi, lo));
+        if (rank < k) {
+            out_ids[(size_t)qi * k + rank].hi = hi;
+            out_ids[(size_t)qi * k + rank].lo = lo;
+            out_dist[(size_t)qi * k + rank] = d;
+        }
+        if (rank == count - 1) s_kth = d;
+    }
+    if (t >= count && t < k) {
+        out_ids[(size_t)qi * k + t].hi = 0ull;
+        out_ids[(size_t)qi * k + t].lo = 0ull;
+        out_dist[(size_t)qi * k + t] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    __syncthreads();
+
+    // 4. completeness proof: no row outside the candidate list can sort before the k-th
+    if (t == 0) {
+        out_counts[qi] = count;
+        int flag = 1;
+        if (n_rows <= (uint32_t)K) {
+            flag = 0;                                  // every live row is a candidate
+        } else if (!prep[qi].zero && !prep[qi].nonfinite) {
+            const uint32_t ord_last = key_ord(s_cand[K - 1]);   // K-th best fast score
+            const double dk = s_kth;
+            if (ord_last == ORD_ALWAYS) flag = 1;      // list flooded by untrusted rows
+            else if (dk != dk) flag = 1;               // k-th is NaN: id order among NaN rows unknown
+            else if (ord_last == ORD_NAN) flag = 0;    // everything outside is a NaN row
+            else {
+                const double bound = (double)ord_to_float(ord_last) + eps;
+                flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
+            }
+        }
+        out_flags[qi] = flag;
+    }
+}
+
+template <typename T>
+static void launch_finalize_t(const void *table, const double *n2, const orx_id *row_ids, const float *q,
+                              const QueryPrep *prep, const uint64_t *partial, int nparts, int slots, int nq,
+                              int k, uint32_t n_rows, double eps, orx_id *out_ids, double *out_dist,
+                              int *out_counts, int *out_flags, cudaStream_t st) {
+    const T *tab = static_cast<const T *>(table);
+    if (slots == 1)
+        finalize_kernel<T, 1><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
+                                                          eps, out_ids, out_dist, out_counts, out_flags);
+    else
+        finalize_kernel<T, 2><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
+                                                          eps, out_ids, out_dist, out_counts, out_flags);
+}
+
+void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,
+                     const float *q, const QueryPrep *prep, const uint64_t *partial, int nparts,
+                     int slots, int nq, int k, uint32_t n_rows, double eps, orx_id *out_ids,
+                     double *out_dist, int *out_counts, int *out_flags, cudaStream_t st) {
+    if (nq <= 0) return;
+    if (dtype == ORX_DTYPE_F32)
+        launch_finalize_t<float>(table, n2, row_ids, q, prep, partial, nparts, slots, nq, k, n_rows, eps,
+                                 out_ids, out_dist, out_counts, out_flags, st);
+    else
+        launch_finalize_t<__nv_bfloat16>(table, n2, row_ids, q, prep, partial, nparts, slots, nq, k, n_rows,
+                                         eps, out_ids, out_dist, out_counts, out_flags, st);
+}
+
+// ----------------------------------------------------------------- merge_topk
+// The on-device step after the allgather of the row-sharded path: n_lists shard results
+// [n_lists][nq][k] -> global top-k per query, same ordering contract.
+constexpr int MERGE_MAX = 1024;
+
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(int n_lists, int nq, int k, const orx_id *__restrict__ ids,
+                  const double *__restrict__ dist, const int *__restrict__ counts,
+                  orx_id *__restrict__ out_ids, double *__restrict__ out_dist,
+                  int *__restrict__ out_counts) {
+    __shared__ double s_d[MERGE_MAX];
+    __shared__ uint64_t s_hi[MERGE_MAX], s_lo[MERGE_MAX];
+    __shared__ unsigned char s_ok[MERGE_MAX];
+    __shared__ int s_valid;
+    const int qi = blockIdx.x;
+    const int total = n_lists * k;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int mine = 0;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int l = e / k, r = e % k;
+        const size_t src = ((size_t)l * nq + qi) * k + r;
+        const bool ok = r < counts[(size_t)l * nq + qi];
+        s_ok[e] = ok;
+        s_d[e] = dist[src];
+        s_hi[e] = ids[src].hi;
+        s_lo[e] = ids[src].lo;
+        mine += ok;
+    }
+    atomicAdd(&s_valid, mine);
+    __syncthreads();
+    const int count = min(k, s_valid);
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        if (!s_ok[e]) continue;
+        int rank = 0;
+        for (int c = 0; c < total; ++c)
+            rank += (c != e && s_ok[c] &&
+                     (sorts_before(s_d[c], s_hi[c], s_lo[c], s_d[e], s_hi[e], s_lo[e]) ||
+                      // identical (distance, id) in two lists (cannot happen with disjoint
+                      // shards): keep a strict total order by list position
+                      (c < e && s_d[c] == s_d[e] && s_hi[c] == s_hi[e] && s_lo[c] == s_lo[e])));
+        if (rank < k) {
+            out_ids[(size_t)qi * k + rank].hi = s_hi[e];
+            out_ids[(size_t)qi * k + rank].lo = s_lo[e];
+            out_dist[(size_t)qi * k + rank] = s_d[e];
+        }
+    }
+    for (int r = count + threadIdx.x; r < k; r += blockDim.x) {
+        out_ids[(size_t)qi * k + r].hi = 0ull;
+        out_ids[(size_t)qi * k + r].lo = 0ull;
+        out_dist[(size_t)qi * k + r] = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    if (threadIdx.x == 0) out_counts[qi] = count;
+}
+
+void launch_merge_topk(int n_lists, int nq, int k, const orx_id *ids, const double *dist,
+                       const int *counts, orx_id *out_ids, double *out_dist, int *out_counts,
+                       cudaStream_t st) {
+    if (nq <= 0) return;
+    merge_topk_kernel<<<nq, 256, 0, st>>>(n_lists, nq, k, ids, dist, counts, out_ids, out_dist,
+                                          out_counts);
+}
+
+// -------------------------------------------------- exhaustive fallback (rare path)
+// collect: every row whose fast score could still reach `fast_floor` (or every row).
+template <typename T>
+__global__ void __launch_bounds__(256)
+collect_kernel(const T *__restrict__ table, const float *__restrict__ scale, uint32_t n_rows,
+               const float *__restrict__ qhat, float fast_floor, int collect_all,
+               uint32_t *__restrict__ list, uint32_t *__restrict__ count) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_gw = gridDim.x * (blockDim.x >> 5);
+    float4 qv[8];
+    load_q_slice<T>(qhat, lane, qv);
+    const uint4 *tab = reinterpret_cast<const uint4 *>(table);
+    for (uint32_t row = gw; row < n_rows; row += n_gw) {
+        bool take = collect_all != 0;
+        if (!take) {
+            uint4 v[RowVec<T>::NV];
+            load_row_vecs<T>(tab, row, lane, v);
+            const float acc = warp_row_dot<T>(v, qv);
+            const uint32_t ord = score_ord(acc, __ldg(scale + row));
+            // NaN rows can only matter when fewer than k finite rows exist; the caller
+            // passes collect_all in that case.
+            take = (ord == ORD_ALWAYS) || (ord != ORD_NAN && ord_to_float(ord) >= fast_floor);
+        }
+        if (take && lane == 0) list[atomicAdd(count, 1u)] = row;
+    }
+}
+
+void launch_collect(int dtype, const void *table, const float *scale, uint32_t n_rows,
+                    const float *qhat, float fast_floor, int collect_all, uint32_t *list,
+                    uint32_t *count, cudaStream_t st) {
+    if (n_rows == 0) return;
+    const int grid = 148 * 4;
+    if (dtype == ORX_DTYPE_F32)
+        collect_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(table), scale, n_rows,
+                                                    qhat, fast_floor, collect_all, list, count);
+    else
+        collect_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16 *>(table), scale, n_rows, qhat, fast_floor, collect_all,
+            list, count);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+rescore_list_kernel(const T *__restrict__ table, const double *__restrict__ n2,
+                    const float *__restrict__ q, const QueryPrep *__restrict__ prep,
+                    const uint32_t *__restrict__ list, const uint32_t *__restrict__ count,
+                    double *__restrict__ dist_out) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_gw = gridDim.x * (blockDim.x >> 5);
+    const uint32_t m = *count;
+    const double n2q = prep->n2q;
+    for (uint32_t i = gw; i < m; i += n_gw) {
+        const uint32_t row = list[i];
+        const double dot = warp_canon_dot<T>(table + (size_t)row * ORX_DIM, q, lane);
+        if (lane == 0) dist_out[i] = canon_dist(dot, n2[row], n2q);
+    }
+}
+
+void launch_rescore_list(int dtype, const void *table, const double *n2, const orx_id *,
+                         const float *q, const QueryPrep *prep, const uint32_t *list,
+                         const uint32_t *count, double *dist_out, cudaStream_t st) {
+    const int grid = 148 * 2;
+    if (dtype == ORX_DTYPE_F32)
+        rescore_list_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(table), n2, q,
+                                                         prep, list, count, dist_out);
+    else
+        rescore_list_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+            static_cast<const __nv_bfloat16 *>(table), n2, q, prep, list, count, dist_out);
+}
+
+// select: k rounds of "smallest entry that sorts strictly after the previous winner".
+__global__ void __launch_bounds__(1024)
+select_list_kernel(const orx_id *__restrict__ row_ids, const uint32_t *__restrict__ list,
+                   const uint32_t *__restrict__ count, const double *__restrict__ dist, int k,
+                   orx_id *__restrict__ out_ids, double *__restrict__ out_dist,
+                   int *__restrict__ out_count) {
+    __shared__ double s_d[1024];
+    __shared__ uint64_t s_hi[1024], s_lo[1024];
+    __shared__ int s_has[1024];
+    const uint32_t m = *count;
+    const int t = threadIdx.x;
+    double pd = 0.0;
+    uint64_t phi = 0, plo = 0;
+    bool have_prev = false;
+    int found = 0;
+    for (int r = 0; r < k; ++r) {
+        double bd = 0.0;
+        uint64_t bhi = 0, blo = 0;
+        bool has = false;
+        for (uint32_t i = t; i < m; i += blockDim.x) {
+            const double d = dist[i];
+            const orx_id id = row_ids[list[i]];
+            if (have_prev && !sorts_before(pd, phi, plo, d, id.hi, id.lo)) continue;
+            if (!has || sorts_before(d, id.hi, id.lo, bd, bhi, blo)) {
+                has = true; bd = d; bhi = id.hi; blo = id.lo;
+            }
+        }
+        s_d[t] = bd; s_hi[t] = bhi; s_lo[t] = blo; s_has[t] = has;
+        __syncthreads();
+        for (int off = 512; off >= 1; off >>= 1) {
+            if (t < off && s_has[t + off] &&
+                (!s_has[t] || sorts_before(s_d[t + off], s_hi[t + off], s_lo[t + off], s_d[t], s_hi[t], s_lo[t]))) {
+                s_d[t] = s_d[t + off]; s_hi[t] = s_hi[t + off]; s_lo[t] = s_lo[t + off]; s_has[t] = 1;
+            }
+            __syncthreads();
+        }
+        const bool any = s_has[0];
+        pd = s_d[0]; phi = s_hi[0]; plo = s_lo[0];
+        __syncthreads();
+        if (!any) break;
+        have_prev = true;
+        if (t == 0) {
+            out_ids[r].hi = phi; out_ids[r].lo = plo; out_dist[r] = pd;
+        }
+        ++found;
+    }
+    if (t == 0) {
+        for (int r = found; r < k; ++r) {
+            out_ids[r].hi = 0; out_ids[r].lo = 0;
+            out_dist[r] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        *out_count = found;
+    }
+}
+
+void launch_select_list(const orx_id *row_ids, const uint32_t *list, const uint32_t *count,
+                        const double *dist, int k, orx_id *out_ids, double *out_dist, int *out_count,
+                        cudaStream_t st) {
+    select_list_kernel<<<1, 1024, 0, st>>>(row_ids, list, count, dist, k, out_ids, out_dist, out_count);
+}
+
+}  // namespace orx

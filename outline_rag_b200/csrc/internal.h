@@ -1,0 +1,70 @@
+// Host-side declarations of the kernel launchers (one .cu per kernel family).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/orx.h"
+
+namespace orx {
+
+// Rigorous bounds on |fast score - canonical cosine| per scan path ("Exactness").
+constexpr double EPS_GEMV_F32 = 3.0e-6;   // fp32 FMA chain of depth 32 + 5 shuffle adds
+constexpr double EPS_GEMV_BF16 = 3.0e-6;  // same arithmetic on exactly-converted bf16 rows
+constexpr double EPS_UMMA_TF32 = 2.1e-3;  // tf32 operand truncation (2 * 2^-10) + fp32 accumulate
+constexpr double EPS_UMMA_BF16 = 4.1e-3;  // bf16 query rounding (2^-8 worst case) + fp32 accumulate
+
+// candidate list = 32 * slots keys per query: k <= 16 -> 32 candidates, k <= 32 -> 64
+inline int slots_for_k(int k) { return k <= 16 ? 1 : 2; }
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+
+struct QueryPrep {            // per query, written by prep_queries
+    double n2q;               // canonical |q|^2
+    int nonfinite;            // 1 if any element is NaN/Inf
+    int zero;                 // 1 if |q| == 0 (every distance is NaN)
+};
+
+// ---- finalize.cu
+void launch_prep_queries(const float *q, int nq, float *qhat, void *qhat_bf16,
+                         QueryPrep *prep, cudaStream_t st);
+void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,
+                     const float *q, const QueryPrep *prep, const uint64_t *partial, int nparts,
+                     int slots, int nq, int k, uint32_t n_rows, double eps,
+                     orx_id *out_ids, double *out_dist, int *out_counts, int *out_flags,
+                     cudaStream_t st);
+void launch_merge_topk(int n_lists, int nq, int k, const orx_id *ids, const double *dist,
+                       const int *counts, orx_id *out_ids, double *out_dist, int *out_counts,
+                       cudaStream_t st);
+// exhaustive fallback: collect rows whose fast score may reach `cos_floor`, rescore, select
+void launch_collect(int dtype, const void *table, const float *scale, uint32_t n_rows,
+                    const float *qhat, float fast_floor, int collect_all,
+                    uint32_t *list, uint32_t *count, cudaStream_t st);
+void launch_rescore_list(int dtype, const void *table, const double *n2, const orx_id *row_ids,
+                         const float *q, const QueryPrep *prep, const uint32_t *list,
+                         const uint32_t *count, double *dist_out, cudaStream_t st);
+void launch_select_list(const orx_id *row_ids, const uint32_t *list, const uint32_t *count,
+                        const double *dist, int k, orx_id *out_ids, double *out_dist,
+                        int *out_count, cudaStream_t st);
+
+// ---- scan_gemv.cu
+int scan_gemv_grid(int device, uint32_t n_rows);
+void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t n_rows,
+                      const float *qhat, int nq, int slots, uint64_t *partial, int grid,
+                      cudaStream_t st);
+
+// ---- table_ops.cu
+void launch_validate_rows(const float *src, uint64_t n, int *flag, cudaStream_t st);
+void launch_commit_rows(int dtype, const float *src, const uint32_t *src_idx, const uint32_t *dst_row,
+                        const orx_id *ids, uint32_t n, void *table, float *scale, double *n2,
+                        orx_id *row_ids, cudaStream_t st);
+void launch_move_rows(int dtype, const uint32_t *src_row, const uint32_t *dst_row, uint32_t n,
+                      void *table, float *scale, double *n2, orx_id *row_ids, cudaStream_t st);
+void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint32_t n, float *out,
+                        cudaStream_t st);
+
+// ---- synth.cu
+void launch_synth_unit(uint64_t key, uint32_t n_vec, float *dst, cudaStream_t st);
+void launch_synth_rows(uint64_t key_noise, uint64_t key_cid, const float *mean, const float *centres,
+                       uint32_t n_centres, uint64_t row_start, uint64_t n_rows, float *dst,
+                       cudaStream_t st);
+
+}  // namespace orx

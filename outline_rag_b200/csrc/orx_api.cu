@@ -1,0 +1,787 @@
+// orx C-ABI (include/orx.h) and the host side of the engine: the device-resident table,
+// the chunk-id -> row map, search orchestration (scan -> finalize -> proof -> fallbacks),
+// upsert / delete planning.  One orx_index = one GPU; sharding lives above (sharded.py).
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "internal.h"
+#include "scan_umma.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(ORX_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+struct IdHash {
+    size_t operator()(const orx_id &a) const {
+        uint64_t z = a.hi * 0x9E3779B97F4A7C15ull ^ a.lo;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return (size_t)(z ^ (z >> 31));
+    }
+};
+struct IdEq {
+    bool operator()(const orx_id &a, const orx_id &b) const { return a.hi == b.hi && a.lo == b.lo; }
+};
+
+bool is_device_ptr(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+size_t elem_size(int dtype) { return dtype == ORX_DTYPE_F32 ? 4 : 2; }
+
+constexpr uint64_t STAGE_ROWS = 65536;   // 256 MB fp32 staging chunk for host uploads
+constexpr int GEMV_QCHUNK = 64;          // queries per gemv launch (partial-list scratch bound)
+
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= n) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        if (e == cudaSuccess) n = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+}  // namespace
+
+struct orx_index {
+    int device = 0;
+    int dtype = ORX_DTYPE_F32;
+    cudaStream_t stream = nullptr;
+    uint64_t capacity = 0;
+    uint64_t n_live = 0;
+    int scan_grid_sms = 148;
+
+    // the table (device)
+    void *table = nullptr;
+    float *scale = nullptr;
+    double *n2 = nullptr;
+    orx_id *row_ids = nullptr;
+
+    // host mirror of the id column + id -> row map
+    std::vector<orx_id> host_row_ids;
+    std::unordered_map<orx_id, uint32_t, IdHash, IdEq> map;
+
+    // search scratch
+    DevBuf<float> q_dev, qhat;
+    DevBuf<__nv_bfloat16> qhat16;
+    DevBuf<orx::QueryPrep> prep;
+    DevBuf<uint64_t> partial;
+    DevBuf<orx_id> res_ids;
+    DevBuf<double> res_dist;
+    DevBuf<int> res_counts, res_flags;
+    PinBuf<float> h_q;
+    PinBuf<orx::QueryPrep> h_prep;
+    PinBuf<orx_id> h_ids;
+    PinBuf<double> h_dist;
+    PinBuf<int> h_counts, h_flags;
+    // exhaustive fallback scratch
+    DevBuf<uint32_t> fb_list, fb_count;
+    DevBuf<double> fb_dist;
+    // upsert / delete scratch
+    DevBuf<float> stage;
+    DevBuf<uint32_t> d_src_idx, d_dst_row;
+    DevBuf<orx_id> d_ids;
+    DevBuf<int> d_flag;
+    PinBuf<uint32_t> h_u32a, h_u32b;
+    PinBuf<int> h_flag;
+
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    orx::UmmaPlan *umma = nullptr;
+    mutable std::mutex mu;
+    orx_stats stats{};
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int alloc_table(orx_index *ix, uint64_t cap) {
+    CK(cudaMalloc(&ix->table, cap * ORX_DIM * elem_size(ix->dtype)));
+    CK(cudaMalloc(&ix->scale, cap * sizeof(float)));
+    CK(cudaMalloc(&ix->n2, cap * sizeof(double)));
+    CK(cudaMalloc(&ix->row_ids, cap * sizeof(orx_id)));
+    ix->capacity = cap;
+    return ORX_OK;
+}
+
+int grow_table(orx_index *ix, uint64_t need) {
+    if (need <= ix->capacity) return ORX_OK;
+    if (need >= 0xFFFFFFFFull) return fail(ORX_ERR_CAPACITY, "table limited to 2^32-2 rows per GPU");
+    uint64_t cap = std::max<uint64_t>(need, ix->capacity + ix->capacity / 2 + 1024);
+    cap = std::min<uint64_t>(cap, 0xFFFFFFFEull);
+    void *t = nullptr;
+    float *s = nullptr;
+    double *n = nullptr;
+    orx_id *r = nullptr;
+    const size_t rb = ORX_DIM * elem_size(ix->dtype);
+    cudaError_t e = cudaMalloc(&t, cap * rb);
+    if (e == cudaSuccess) e = cudaMalloc(&s, cap * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&n, cap * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&r, cap * sizeof(orx_id));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        if (t) cudaFree(t);
+        if (s) cudaFree(s);
+        if (n) cudaFree(n);
+        if (r) cudaFree(r);
+        return fail(ORX_ERR_CAPACITY, "cannot grow table to %llu rows: %s", (unsigned long long)cap,
+                    cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(t, ix->table, ix->n_live * rb, cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaMemcpyAsync(s, ix->scale, ix->n_live * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaMemcpyAsync(n, ix->n2, ix->n_live * sizeof(double), cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaMemcpyAsync(r, ix->row_ids, ix->n_live * sizeof(orx_id), cudaMemcpyDeviceToDevice, ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    cudaFree(ix->table);
+    cudaFree(ix->scale);
+    cudaFree(ix->n2);
+    cudaFree(ix->row_ids);
+    ix->table = t;
+    ix->scale = s;
+    ix->n2 = n;
+    ix->row_ids = r;
+    ix->capacity = cap;
+    if (ix->umma) orx::umma_plan_invalidate(ix->umma);
+    return ORX_OK;
+}
+
+// ---------------------------------------------------------------- search core
+struct SearchOut {          // where the results of query j go (device pointers)
+    orx_id *ids;
+    double *dist;
+    int *counts;
+};
+
+int exhaustive_query(orx_index *ix, int qi, int k, double dk, bool force_all, const SearchOut &out) {
+    // Collect every row that could sort at or before the current k-th candidate, rescore all of
+    // them canonically, select the k best.  Always exact; cost grows with the number of near-ties.
+    const uint32_t n_rows = (uint32_t)ix->n_live;
+    CK(ix->fb_list.ensure(ix->capacity));
+    CK(ix->fb_dist.ensure(ix->capacity));
+    CK(ix->fb_count.ensure(1));
+    const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
+    bool all = force_all || !(dk == dk) || dk >= 2.0;
+    float floor_f = 0.f;
+    if (!all) {
+        floor_f = (float)((1.0 - dk) - eps);
+        floor_f = nextafterf(floor_f, -INFINITY);     // conversion may have rounded up
+    }
+    CK(cudaMemsetAsync(ix->fb_count.p, 0, sizeof(uint32_t), ix->stream));
+    orx::launch_collect(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qi * ORX_DIM, floor_f,
+                        all ? 1 : 0, ix->fb_list.p, ix->fb_count.p, ix->stream);
+    orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, ix->q_dev.p + (size_t)qi * ORX_DIM,
+                             ix->prep.p + qi, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, ix->stream);
+    orx::launch_select_list(ix->row_ids, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, k,
+                            out.ids + (size_t)qi * k, out.dist + (size_t)qi * k, out.counts + qi, ix->stream);
+    ix->stats.kernel_launches += 3;
+    ix->stats.fallback_exhaustive += 1;
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int gemv_pass(orx_index *ix, int q0, int nq, int k, const SearchOut &out, int *flags_dev) {
+    const uint32_t n_rows = (uint32_t)ix->n_live;
+    const int grid = orx::scan_gemv_grid(ix->device, n_rows);
+    const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
+    const int slots = orx::slots_for_k(k);
+    for (int s = 0; s < nq; s += GEMV_QCHUNK) {
+        const int m = std::min(GEMV_QCHUNK, nq - s);
+        const int qa = q0 + s;
+        CK(ix->partial.ensure((size_t)m * grid * 32 * slots));
+        orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qa * ORX_DIM, m,
+                              slots, ix->partial.p, grid, ix->stream);
+        orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, ix->q_dev.p + (size_t)qa * ORX_DIM,
+                             ix->prep.p + qa, ix->partial.p, grid, slots, m, k, n_rows, eps,
+                             out.ids + (size_t)qa * k, out.dist + (size_t)qa * k, out.counts + qa,
+                             flags_dev + qa, ix->stream);
+        ix->stats.kernel_launches += 2;
+    }
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
+                  int *out_counts) {
+    const bool q_on_dev = is_device_ptr(queries);
+    const bool out_on_dev = is_device_ptr(out_ids);
+    if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
+        return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
+    cudaStream_t st = ix->stream;
+    const size_t nk = (size_t)nq * k;
+
+    CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
+    CK(ix->qhat.ensure((size_t)nq * ORX_DIM));
+    CK(ix->qhat16.ensure((size_t)nq * ORX_DIM));
+    CK(ix->prep.ensure(nq));
+    CK(ix->res_flags.ensure(nq));
+    CK(ix->h_prep.ensure(nq));
+    CK(ix->h_flags.ensure(nq));
+    CK(ix->h_ids.ensure(nk));
+    CK(ix->h_dist.ensure(nk));
+    CK(ix->h_counts.ensure(nq));
+    if (!out_on_dev) {
+        CK(ix->res_ids.ensure(nk));
+        CK(ix->res_dist.ensure(nk));
+        CK(ix->res_counts.ensure(nq));
+    }
+    SearchOut out{out_on_dev ? out_ids : ix->res_ids.p, out_on_dev ? out_dist : ix->res_dist.p,
+                  out_on_dev ? out_counts : ix->res_counts.p};
+
+    CK(cudaEventRecord(ix->ev[0], st));
+    if (q_on_dev) {
+        CK(cudaMemcpyAsync(ix->q_dev.p, queries, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
+        memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
+        CK(cudaMemcpyAsync(ix->q_dev.p, ix->h_q.p, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+    }
+    orx::launch_prep_queries(ix->q_dev.p, nq, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+    ix->stats.kernel_launches += 1;
+
+    const uint32_t n_rows = (uint32_t)ix->n_live;
+    int path = 1;
+    CK(cudaEventRecord(ix->ev[1], st));
+    if (n_rows == 0) {
+        CK(cudaMemsetAsync(out.ids, 0, nk * sizeof(orx_id), st));
+        CK(cudaMemsetAsync(out.dist, 0xFF, nk * sizeof(double), st));   // all-ones = NaN
+        CK(cudaMemsetAsync(out.counts, 0, nq * sizeof(int), st));
+        CK(cudaMemsetAsync(ix->res_flags.p, 0, nq * sizeof(int), st));
+    } else if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
+        path = 2;
+        int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
+                                  ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
+                                  out.counts, ix->res_flags.p, st, &ix->stats.kernel_launches);
+        if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
+    } else {
+        int rc = gemv_pass(ix, 0, nq, k, out, ix->res_flags.p);
+        if (rc != ORX_OK) return rc;
+    }
+    CK(cudaEventRecord(ix->ev[2], st));
+
+    // read back what the host must see to decide on fallbacks
+    CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ix->h_flags.p, ix->res_flags.p, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ix->h_dist.p, out.dist, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(ix->h_counts.p, out.counts, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (!out_on_dev) CK(cudaMemcpyAsync(ix->h_ids.p, out.ids, nk * sizeof(orx_id), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+
+    for (int j = 0; j < nq; ++j)
+        if (ix->h_prep.p[j].nonfinite)
+            return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+
+    bool any_fb = false;
+    if (n_rows > 0) {
+        // level 1: coarse tensor-core pass unproven -> exact fp32 scan for those queries
+        if (path == 2) {
+            for (int j = 0; j < nq; ++j) {
+                if (!ix->h_flags.p[j]) continue;
+                any_fb = true;
+                ix->stats.fallback_gemv += 1;
+                int rc = gemv_pass(ix, j, 1, k, out, ix->res_flags.p);
+                if (rc != ORX_OK) return rc;
+            }
+            if (any_fb) {
+                CK(cudaMemcpyAsync(ix->h_flags.p, ix->res_flags.p, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ix->h_dist.p, out.dist, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ix->h_counts.p, out.counts, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        }
+        // level 2: still unproven (dense near-ties, NaN rows, zero query) -> exhaustive collect
+        for (int j = 0; j < nq; ++j) {
+            if (!ix->h_flags.p[j]) continue;
+            any_fb = true;
+            const int cnt = ix->h_counts.p[j];
+            const bool force_all = ix->h_prep.p[j].zero || cnt < k;
+            const double dk = cnt > 0 ? ix->h_dist.p[(size_t)j * k + cnt - 1] : NAN;
+            int rc = exhaustive_query(ix, j, k, dk, force_all, out);
+            if (rc != ORX_OK) return rc;
+        }
+    }
+    CK(cudaEventRecord(ix->ev[3], st));
+    if (any_fb) {
+        if (!out_on_dev) {
+            CK(cudaMemcpyAsync(ix->h_ids.p, out.ids, nk * sizeof(orx_id), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ix->h_dist.p, out.dist, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ix->h_counts.p, out.counts, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    CK(cudaStreamSynchronize(st));
+    if (!out_on_dev) {
+        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
+        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
+        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
+    }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]) == cudaSuccess) ix->stats.last_scan_ms = ms;
+    if (cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]) == cudaSuccess) ix->stats.last_search_ms = ms;
+    cudaGetLastError();
+    ix->stats.last_path = path;
+    ix->stats.searches += 1;
+    ix->stats.queries += nq;
+    return ORX_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C-ABI
+extern "C" {
+
+const char *orx_last_error(void) { return g_err.c_str(); }
+const char *orx_version(void) { return "orx 0.1 (sm_100a)"; }
+
+int orx_create(orx_index **out, int dim, int dtype, uint64_t capacity_rows, int device) {
+    if (!out) return fail(ORX_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "expected %d dimensions, not %d", ORX_DIM, dim);
+    if (dtype != ORX_DTYPE_F32 && dtype != ORX_DTYPE_BF16) return fail(ORX_ERR_INVALID, "unknown dtype %d", dtype);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(ORX_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(ORX_ERR_INVALID, "device %d out of range (%d present)", device, ndev);
+    DeviceGuard g(device);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(ORX_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                    prop.major, prop.minor);
+    orx_index *ix = new orx_index();
+    ix->device = device;
+    ix->dtype = dtype;
+    ix->scan_grid_sms = prop.multiProcessorCount;
+    uint64_t cap = std::max<uint64_t>(capacity_rows, 1024);
+    if (cap >= 0xFFFFFFFFull) {
+        delete ix;
+        return fail(ORX_ERR_CAPACITY, "table limited to 2^32-2 rows per GPU");
+    }
+    int rc = alloc_table(ix, cap);
+    if (rc != ORX_OK) {
+        orx_destroy(ix);
+        return rc;
+    }
+    for (auto &e : ix->ev) {
+        cudaError_t ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) {
+            orx_destroy(ix);
+            return fail(ORX_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce));
+        }
+    }
+    ix->umma = orx::umma_plan_create(device);
+    ix->host_row_ids.reserve(cap);
+    ix->map.reserve(cap);
+    *out = ix;
+    return ORX_OK;
+}
+
+void orx_destroy(orx_index *ix) {
+    if (!ix) return;
+    DeviceGuard g(ix->device);
+    cudaDeviceSynchronize();
+    if (ix->umma) orx::umma_plan_destroy(ix->umma);
+    cudaFree(ix->table);
+    cudaFree(ix->scale);
+    cudaFree(ix->n2);
+    cudaFree(ix->row_ids);
+    ix->q_dev.release(); ix->qhat.release(); ix->qhat16.release(); ix->prep.release(); ix->partial.release();
+    ix->res_ids.release(); ix->res_dist.release(); ix->res_counts.release(); ix->res_flags.release();
+    ix->h_q.release(); ix->h_prep.release(); ix->h_ids.release(); ix->h_dist.release();
+    ix->h_counts.release(); ix->h_flags.release();
+    ix->fb_list.release(); ix->fb_count.release(); ix->fb_dist.release();
+    ix->stage.release(); ix->d_src_idx.release(); ix->d_dst_row.release(); ix->d_ids.release();
+    ix->d_flag.release(); ix->h_u32a.release(); ix->h_u32b.release(); ix->h_flag.release();
+    for (auto &e : ix->ev)
+        if (e) cudaEventDestroy(e);
+    cudaGetLastError();
+    delete ix;
+}
+
+int orx_set_stream(orx_index *ix, void *cuda_stream) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStreamSynchronize(ix->stream);
+    ix->stream = static_cast<cudaStream_t>(cuda_stream);
+    return ORX_OK;
+}
+
+uint64_t orx_size(const orx_index *ix) {
+    if (!ix) return 0;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return ix->n_live;
+}
+uint64_t orx_capacity(const orx_index *ix) {
+    if (!ix) return 0;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return ix->capacity;
+}
+int orx_dtype(const orx_index *ix) { return ix ? ix->dtype : -1; }
+
+int orx_get_stats(const orx_index *ix, orx_stats *out) {
+    if (!ix || !out) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    *out = ix->stats;
+    return ORX_OK;
+}
+
+int orx_contains(const orx_index *ix, orx_id id) {
+    if (!ix) return 0;
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return ix->map.find(id) != ix->map.end() ? 1 : 0;
+}
+
+int orx_upsert(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t n, int dim) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "expected %d dimensions, not %d", ORX_DIM, dim);
+    if (n == 0) return ORX_OK;
+    if (!ids || !vecs) return fail(ORX_ERR_INVALID, "null ids/vecs");
+    if (is_device_ptr(ids)) return fail(ORX_ERR_INVALID, "ids must be a host pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const bool on_dev = is_device_ptr(vecs);
+    const uint64_t chunk = std::min<uint64_t>(n, STAGE_ROWS);
+
+    CK(ix->d_flag.ensure(1));
+    CK(ix->h_flag.ensure(1));
+    if (!on_dev) CK(ix->stage.ensure(chunk * ORX_DIM));
+
+    // ---- phase 1: pgvector's element check over the WHOLE batch before anything is written
+    CK(cudaMemsetAsync(ix->d_flag.p, 0, sizeof(int), st));
+    for (uint64_t s = 0; s < n; s += chunk) {
+        const uint64_t m = std::min(chunk, n - s);
+        const float *src = vecs + s * ORX_DIM;
+        if (!on_dev) {
+            CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            src = ix->stage.p;
+        }
+        orx::launch_validate_rows(src, m, ix->d_flag.p, st);
+        ix->stats.kernel_launches += 1;
+    }
+    CK(cudaMemcpyAsync(ix->h_flag.p, ix->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
+
+    // ---- phase 2: plan destinations (existing id -> its row, new id -> append; last duplicate wins)
+    uint64_t n_new = 0;
+    {
+        std::unordered_map<orx_id, int, IdHash, IdEq> seen;
+        if (n > 1) seen.reserve(n);
+        for (uint64_t i = 0; i < n; ++i)
+            if (ix->map.find(ids[i]) == ix->map.end() && seen.emplace(ids[i], 1).second) ++n_new;
+    }
+    int rc = grow_table(ix, ix->n_live + n_new);
+    if (rc != ORX_OK) return rc;
+
+    CK(ix->d_src_idx.ensure(chunk));
+    CK(ix->d_dst_row.ensure(chunk));
+    CK(ix->d_ids.ensure(chunk));
+    CK(ix->h_u32a.ensure(chunk));
+    CK(ix->h_u32b.ensure(chunk));
+    const bool single = (n <= chunk);      // staged data of phase 1 is still resident
+    for (uint64_t s = 0; s < n; s += chunk) {
+        const uint64_t m = std::min(chunk, n - s);
+        // plan this chunk; an id repeated inside the chunk keeps the later source row
+        std::unordered_map<uint32_t, uint32_t> slot_of_row;   // dst row -> plan slot
+        uint32_t np = 0;
+        for (uint64_t i = 0; i < m; ++i) {
+            const orx_id id = ids[s + i];
+            uint32_t row;
+            auto it = ix->map.find(id);
+            if (it != ix->map.end()) row = it->second;
+            else {
+                row = (uint32_t)ix->n_live++;
+                ix->map.emplace(id, row);
+                if (ix->host_row_ids.size() <= row) ix->host_row_ids.resize((size_t)row + 1);
+                ix->host_row_ids[row] = id;
+            }
+            auto ps = slot_of_row.find(row);
+            if (ps != slot_of_row.end()) ix->h_u32a.p[ps->second] = (uint32_t)i;
+            else {
+                slot_of_row.emplace(row, np);
+                ix->h_u32a.p[np] = (uint32_t)i;
+                ix->h_u32b.p[np] = row;
+                ++np;
+            }
+        }
+        const float *src = vecs + s * ORX_DIM;
+        if (!on_dev) {
+            if (!single)
+                CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            src = ix->stage.p;
+        }
+        CK(cudaMemcpyAsync(ix->d_src_idx.p, ix->h_u32a.p, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_dst_row.p, ix->h_u32b.p, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_ids.p, ids + s, m * sizeof(orx_id), cudaMemcpyHostToDevice, st));
+        orx::launch_commit_rows(ix->dtype, src, ix->d_src_idx.p, ix->d_dst_row.p, ix->d_ids.p, np, ix->table,
+                                ix->scale, ix->n2, ix->row_ids, st);
+        ix->stats.kernel_launches += 1;
+        CK(cudaStreamSynchronize(st));     // h_u32a/b and the caller's buffers are reused next chunk
+    }
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed) {
+    if (n_removed) *n_removed = 0;
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n == 0) return ORX_OK;
+    if (!ids) return fail(ORX_ERR_INVALID, "null ids");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+
+    std::vector<uint32_t> doomed;
+    doomed.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        auto it = ix->map.find(ids[i]);
+        if (it == ix->map.end()) continue;        // unknown id: ignored, like the SQL DELETE
+        doomed.push_back(it->second);
+        ix->map.erase(it);                        // also drops a repeated id in the same call
+    }
+    const uint64_t d = doomed.size();
+    if (d == 0) return ORX_OK;
+    const uint64_t new_live = ix->n_live - d;
+    // holes below the new end are filled by the surviving rows above it
+    std::vector<char> dead_tail(d, 0);            // rows in [new_live, n_live) that are deleted
+    std::vector<uint32_t> holes;
+    for (uint32_t r : doomed) {
+        if (r >= new_live) dead_tail[r - new_live] = 1;
+        else holes.push_back(r);
+    }
+    CK(ix->h_u32a.ensure(std::max<size_t>(holes.size(), 1)));
+    CK(ix->h_u32b.ensure(std::max<size_t>(holes.size(), 1)));
+    size_t hmv = 0;
+    for (uint64_t r = new_live; r < ix->n_live && hmv < holes.size(); ++r) {
+        if (dead_tail[r - new_live]) continue;
+        const uint32_t dst = holes[hmv];
+        ix->h_u32a.p[hmv] = (uint32_t)r;
+        ix->h_u32b.p[hmv] = dst;
+        const orx_id moved = ix->host_row_ids[r];
+        ix->host_row_ids[dst] = moved;
+        ix->map[moved] = dst;
+        ++hmv;
+    }
+    ix->host_row_ids.resize(new_live);
+    ix->n_live = new_live;
+    if (hmv > 0) {
+        CK(ix->d_src_idx.ensure(hmv));
+        CK(ix->d_dst_row.ensure(hmv));
+        CK(cudaMemcpyAsync(ix->d_src_idx.p, ix->h_u32a.p, hmv * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_dst_row.p, ix->h_u32b.p, hmv * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        orx::launch_move_rows(ix->dtype, ix->d_src_idx.p, ix->d_dst_row.p, (uint32_t)hmv, ix->table, ix->scale,
+                              ix->n2, ix->row_ids, st);
+        ix->stats.kernel_launches += 1;
+        ix->stats.rows_moved += hmv;
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+    }
+    if (n_removed) *n_removed = d;
+    return ORX_OK;
+}
+
+int orx_search(orx_index *ix, const float *queries, int nq, int dim, int k, orx_id *out_ids, double *out_dist,
+               int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "different vector dimensions %d and %d", ORX_DIM, dim);
+    if (k < 1 || k > ORX_MAX_K) return fail(ORX_ERR_INVALID, "k must be in [1, %d], got %d", ORX_MAX_K, k);
+    if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
+    if (nq == 0) return ORX_OK;
+    if (!queries || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    return search_locked(ix, queries, nq, k, out_ids, out_dist, out_counts);
+}
+
+int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids, const double *dist,
+                   const int *counts, orx_id *out_ids, double *out_dist, int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n_lists < 1 || nq < 0 || k < 1 || k > ORX_MAX_K || (size_t)n_lists * k > 1024)
+        return fail(ORX_ERR_INVALID, "bad merge shape (n_lists=%d, nq=%d, k=%d)", n_lists, nq, k);
+    if (nq == 0) return ORX_OK;
+    if (!ids || !dist || !counts || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const bool in_dev = is_device_ptr(ids), out_dev = is_device_ptr(out_ids);
+    const size_t nin = (size_t)n_lists * nq * k, nout = (size_t)nq * k;
+    if (in_dev && out_dev) {
+        orx::launch_merge_topk(n_lists, nq, k, ids, dist, counts, out_ids, out_dist, out_counts, st);
+        ix->stats.kernel_launches += 1;
+        CK(cudaGetLastError());
+        return ORX_OK;
+    }
+    if (in_dev || out_dev) return fail(ORX_ERR_INVALID, "merge inputs and outputs must live on the same side");
+    // host buffers: stage through device scratch (the merge itself always runs on the GPU)
+    orx_id *d_ids = nullptr, *d_oids = nullptr;
+    double *d_dist = nullptr, *d_odist = nullptr;
+    int *d_cnt = nullptr, *d_ocnt = nullptr;
+    CK(cudaMalloc(&d_ids, nin * sizeof(orx_id)));
+    CK(cudaMalloc(&d_dist, nin * sizeof(double)));
+    CK(cudaMalloc(&d_cnt, (size_t)n_lists * nq * sizeof(int)));
+    CK(cudaMalloc(&d_oids, nout * sizeof(orx_id)));
+    CK(cudaMalloc(&d_odist, nout * sizeof(double)));
+    CK(cudaMalloc(&d_ocnt, nq * sizeof(int)));
+    CK(cudaMemcpyAsync(d_ids, ids, nin * sizeof(orx_id), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_dist, dist, nin * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d_cnt, counts, (size_t)n_lists * nq * sizeof(int), cudaMemcpyHostToDevice, st));
+    orx::launch_merge_topk(n_lists, nq, k, d_ids, d_dist, d_cnt, d_oids, d_odist, d_ocnt, st);
+    ix->stats.kernel_launches += 1;
+    CK(cudaMemcpyAsync(out_ids, d_oids, nout * sizeof(orx_id), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_dist, d_odist, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_counts, d_ocnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    cudaFree(d_ids); cudaFree(d_dist); cudaFree(d_cnt); cudaFree(d_oids); cudaFree(d_odist); cudaFree(d_ocnt);
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int orx_fetch(orx_index *ix, const orx_id *ids, uint64_t n, float *out_vecs, int *out_found) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n == 0) return ORX_OK;
+    if (!ids || !out_vecs || !out_found) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const uint64_t chunk = std::min<uint64_t>(n, STAGE_ROWS);
+    CK(ix->stage.ensure(chunk * ORX_DIM));
+    CK(ix->d_src_idx.ensure(chunk));
+    CK(ix->h_u32a.ensure(chunk));
+    for (uint64_t s = 0; s < n; s += chunk) {
+        const uint64_t m = std::min(chunk, n - s);
+        for (uint64_t i = 0; i < m; ++i) {
+            auto it = ix->map.find(ids[s + i]);
+            out_found[s + i] = it != ix->map.end();
+            ix->h_u32a.p[i] = it != ix->map.end() ? it->second : 0xFFFFFFFFu;
+        }
+        CK(cudaMemcpyAsync(ix->d_src_idx.p, ix->h_u32a.p, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        orx::launch_gather_rows(ix->dtype, ix->table, ix->d_src_idx.p, (uint32_t)m, ix->stage.p, st);
+        ix->stats.kernel_launches += 1;
+        CK(cudaMemcpyAsync(out_vecs + s * ORX_DIM, ix->stage.p, m * ORX_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+namespace {
+struct SynthState {
+    float *mean = nullptr, *centres = nullptr;
+};
+std::mutex g_synth_mu;
+std::map<std::tuple<int, uint64_t, uint32_t>, SynthState> g_synth;
+}  // namespace
+
+namespace orx { uint64_t synth_stream_key(uint64_t seed, uint64_t tag); }
+
+int orx_synth_rows(int device, void *cuda_stream, uint64_t seed, uint32_t n_centres, uint64_t row_start,
+                   uint64_t n_rows, float *dst_device) {
+    if (n_centres == 0) return fail(ORX_ERR_INVALID, "n_centres must be > 0");
+    if (n_rows == 0) return ORX_OK;
+    if (!is_device_ptr(dst_device)) return fail(ORX_ERR_INVALID, "dst must be a device pointer");
+    DeviceGuard g(device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    // stream tags: outline_rag_b200/synth.py TAG_*
+    const uint64_t k_mean = orx::synth_stream_key(seed, 0x6D65616Eull);
+    const uint64_t k_centre = orx::synth_stream_key(seed, 0x63656E74ull);
+    const uint64_t k_noise = orx::synth_stream_key(seed, 0x6E6F6973ull);
+    const uint64_t k_cid = orx::synth_stream_key(seed, 0x63696421ull);
+    SynthState ss;
+    {
+        std::lock_guard<std::mutex> lk(g_synth_mu);
+        auto key = std::make_tuple(device, seed, n_centres);
+        auto it = g_synth.find(key);
+        if (it == g_synth.end()) {
+            CK(cudaMalloc(&ss.mean, ORX_DIM * sizeof(float)));
+            CK(cudaMalloc(&ss.centres, (size_t)n_centres * ORX_DIM * sizeof(float)));
+            orx::launch_synth_unit(k_mean, 1, ss.mean, st);
+            orx::launch_synth_unit(k_centre, n_centres, ss.centres, st);
+            CK(cudaStreamSynchronize(st));
+            g_synth.emplace(key, ss);
+        } else ss = it->second;
+    }
+    orx::launch_synth_rows(k_noise, k_cid, ss.mean, ss.centres, n_centres, row_start, n_rows, dst_device, st);
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+}  // extern "C"

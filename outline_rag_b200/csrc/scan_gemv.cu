@@ -1,0 +1,114 @@
+// scan_gemv: the single-query sequential scan -- HBM-bound GEMV with a fused top-K select.
+//
+// Stands in for the per-row `cosine_distance(row.embedding, q)` + top-N heapsort that the
+// Postgres executor runs for `ORDER BY embedding <=> :q LIMIT :k`
+// (pgvector src/vector.c [UPSTREAM]; SQL reached from reference app/rag.py:85-87).
+//
+// Layout / schedule (DESIGN.md "scan_gemv"):
+//   * persistent grid: 2 CTAs x 8 warps per SM, one warp per row, ROWS_PER_ITER rows per
+//     warp in flight; a warp's rows are consecutive so each warp streams 8 KB contiguous,
+//     and the whole grid walks the table front to back (DRAM page locality);
+//   * 128-bit ld.global.nc.L1::no_allocate loads, lane l owns elements 4*(l+32j)..+3
+//     (fp32) or 8*(l+32j)..+7 (bf16) and keeps the matching slice of the normalised query
+//     in 32 registers;
+//   * fp32 FMA chain per lane + xor-butterfly -> every lane has the dot; score = dot*scale[row];
+//   * one compare per row against the warp's running K-th best; the rare insert shifts a
+//     register-resident sorted list spread over the 32 lanes (common.cuh WarpTopK);
+//   * per-CTA merge in shared memory -> partial[query][cta][KC] (sorted keys).
+// Algorithmic bytes per launch: n_rows * 1024 * sizeof(elem) (+4 B/row scale, <0.1%).
+#include "scan_common.cuh"
+#include "internal.h"
+
+namespace orx {
+
+constexpr int ROWS_PER_ITER = 2;
+
+template <typename T, int S>
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
+scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, uint32_t n_rows,
+                 const float *__restrict__ qhat_all, uint64_t *__restrict__ partial_all) {
+    constexpr int NV = RowVec<T>::NV;
+    constexpr int K = 32 * S;
+    __shared__ uint64_t s_keys[SCAN_WARPS][K];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int query = blockIdx.y;
+    const float *qhat = qhat_all + (size_t)query * ORX_DIM;
+    uint64_t *partial = partial_all + ((size_t)query * gridDim.x + blockIdx.x) * K;
+
+    float4 qv[8];
+    load_q_slice<T>(qhat, lane, qv);
+
+    WarpTopK<S> top;
+    top.init();
+
+    const uint4 *tab = reinterpret_cast<const uint4 *>(table);
+    const uint32_t gw = blockIdx.x * SCAN_WARPS + warp;
+    const uint32_t n_gw = gridDim.x * SCAN_WARPS;
+    const uint32_t n_chunks = (n_rows + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
+
+    for (uint32_t c = gw; c < n_chunks; c += n_gw) {
+        uint4 v[ROWS_PER_ITER][NV];
+        float sc[ROWS_PER_ITER];
+        const uint32_t row0 = c * ROWS_PER_ITER;
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_ITER; ++r) {
+            const uint32_t rr = min(row0 + r, n_rows - 1);   // tail rows re-read the last row
+            load_row_vecs<T>(tab, rr, lane, v[r]);
+            sc[r] = __ldg(scale + rr);
+        }
+#pragma unroll
+        for (int r = 0; r < ROWS_PER_ITER; ++r) {
+            const float acc = warp_row_dot<T>(v[r], qv);
+            const uint32_t row = row0 + r;
+            if (row < n_rows) top.offer(make_key(score_ord(acc, sc[r]), row), lane);
+        }
+    }
+
+    // per-CTA merge: warp 0 folds the other warps' sorted lists into its own
+    top.store(s_keys[warp], lane);
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < SCAN_WARPS; ++w) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                // lists are sorted: once a slot's best key fails, later slots fail too
+                top.offer_lanes(s_keys[w][s * 32 + lane], lane);
+            }
+        }
+        top.store(partial, lane);
+    }
+}
+
+int scan_gemv_grid(int device, uint32_t n_rows) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    uint32_t chunks = (n_rows + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
+    uint32_t want = (chunks + SCAN_WARPS - 1) / SCAN_WARPS;
+    uint32_t full = (uint32_t)sms * 2u;
+    uint32_t g = want < full ? want : full;
+    return g < 1 ? 1 : (int)g;
+}
+
+template <typename T>
+static void launch_scan_gemv_t(const void *table, const float *scale, uint32_t n_rows, const float *qhat,
+                               int nq, int slots, uint64_t *partial, int grid, cudaStream_t st) {
+    dim3 g(grid, nq);
+    const T *tab = static_cast<const T *>(table);
+    if (slots == 1)
+        scan_gemv_kernel<T, 1><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial);
+    else
+        scan_gemv_kernel<T, 2><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial);
+}
+
+void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t n_rows,
+                      const float *qhat, int nq, int slots, uint64_t *partial, int grid,
+                      cudaStream_t st) {
+    if (dtype == ORX_DTYPE_F32)
+        launch_scan_gemv_t<float>(table, scale, n_rows, qhat, nq, slots, partial, grid, st);
+    else
+        launch_scan_gemv_t<__nv_bfloat16>(table, scale, n_rows, qhat, nq, slots, partial, grid, st);
+}
+
+}  // namespace orx

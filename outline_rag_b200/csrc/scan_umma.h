@@ -1,0 +1,25 @@
+// tcgen05 / TMEM batched scan (scan_umma.cu): host-side interface.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include "internal.h"
+
+namespace orx {
+
+struct UmmaPlan;
+
+UmmaPlan *umma_plan_create(int device);
+void umma_plan_destroy(UmmaPlan *p);
+void umma_plan_invalidate(UmmaPlan *p);          // table was reallocated: tensor maps are stale
+bool umma_should_use(const UmmaPlan *p, int nq, uint32_t n_rows);
+const char *umma_last_error();
+
+// Coarse tensor-core scan + finalize for nq queries; writes results and per-query proof flags.
+int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, const double *n2,
+                const orx_id *row_ids, uint32_t n_rows, const float *q_dev, const float *qhat,
+                const __nv_bfloat16 *qhat16, const QueryPrep *prep, int nq, int k, orx_id *out_ids,
+                double *out_dist, int *out_counts, int *out_flags, cudaStream_t st,
+                uint64_t *launch_counter);
+
+}  // namespace orx
