@@ -57,6 +57,8 @@ typedef struct orx_stats {
     float    last_search_ms;      /* device time of the last search, first to last kernel */
     int      last_path;           /* 0 none, 1 gemv scan, 2 tcgen05 scan           */
     int      reserved;
+    uint64_t scan_launches;       /* scan kernel launches (gemv or tcgen05)        */
+    double   scan_ms_total;       /* sum of their device times (CUDA events around each launch) */
 } orx_stats;
 
 /* Replaces `AsyncPGVectorStore.create(engine, embedding_service,

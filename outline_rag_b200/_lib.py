@@ -1,0 +1,128 @@
+"""ctypes binding of the C-ABI in ``include/orx.h`` (``liborx.so``, built in-tree).
+
+There is NO CPU fallback: if the shared library is missing or cannot be loaded the
+import of this module raises, and every entry point needs a B200 at call time
+(``orx_create`` fails with ORX_ERR_CUDA otherwise).  Loading the library and
+resolving its symbols does not need a GPU (``tests/test_abi.py``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liborx.so")
+CSRC_DIR = os.path.join(_HERE, "csrc")
+
+ORX_DIM = 1024
+ORX_MAX_K = 32
+DTYPE_F32 = 0
+DTYPE_BF16 = 1
+
+ORX_OK = 0
+ORX_ERR_INVALID = -1
+ORX_ERR_DIM = -2
+ORX_ERR_NONFINITE = -3
+ORX_ERR_CUDA = -4
+ORX_ERR_CAPACITY = -5
+
+
+class OrxError(RuntimeError):
+    """Raised for every non-zero return of the C-ABI; ``code`` is the ORX_ERR_* value."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"orx error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class OrxValueError(OrxError, ValueError):
+    """ORX_ERR_DIM / ORX_ERR_NONFINITE / ORX_ERR_INVALID: the input is at fault (pgvector
+    raises `expected 1024 dimensions` / `NaN not allowed in vector` for the same inputs)."""
+
+
+class OrxId(C.Structure):
+    _fields_ = [("hi", C.c_uint64), ("lo", C.c_uint64)]
+
+
+class OrxStats(C.Structure):
+    _fields_ = [
+        ("kernel_launches", C.c_uint64),
+        ("searches", C.c_uint64),
+        ("queries", C.c_uint64),
+        ("fallback_gemv", C.c_uint64),
+        ("fallback_exhaustive", C.c_uint64),
+        ("rows_moved", C.c_uint64),
+        ("last_scan_ms", C.c_float),
+        ("last_search_ms", C.c_float),
+        ("last_path", C.c_int),
+        ("reserved", C.c_int),
+        ("scan_launches", C.c_uint64),
+        ("scan_ms_total", C.c_double),
+    ]
+
+
+# name -> (restype, argtypes); every symbol include/orx.h declares
+_vp = C.c_void_p
+SIGNATURES = {
+    "orx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "orx_destroy": (None, [_vp]),
+    "orx_set_stream": (C.c_int, [_vp, _vp]),
+    "orx_size": (C.c_uint64, [_vp]),
+    "orx_capacity": (C.c_uint64, [_vp]),
+    "orx_dtype": (C.c_int, [_vp]),
+    "orx_get_stats": (C.c_int, [_vp, C.POINTER(OrxStats)]),
+    "orx_upsert": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int]),
+    "orx_delete": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "orx_contains": (C.c_int, [_vp, OrxId]),
+    "orx_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "orx_merge_topk": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "orx_fetch": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp]),
+    "orx_synth_rows": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp]),
+    "orx_last_error": (C.c_char_p, []),
+    "orx_version": (C.c_char_p, []),
+}
+
+
+def build(verbose: bool = False) -> str:
+    """Compile ``liborx.so`` for sm_100a with the in-tree Makefile (nvcc cross-compiles
+    without a GPU).  Returns the library path."""
+    out = subprocess.run(["make", "-C", CSRC_DIR, "-j8"], capture_output=True, text=True)
+    if verbose or out.returncode != 0:
+        print(out.stdout)
+        print(out.stderr)
+    if out.returncode != 0:
+        raise RuntimeError("building liborx.so failed (see output above)")
+    return LIB_PATH
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `make -C {CSRC_DIR}` "
+            "(or __graft_entry__.build()).  outline_rag_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the header and the library diverge
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    msg = lib.orx_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc: int) -> None:
+    if rc != ORX_OK:
+        cls = OrxValueError if rc in (ORX_ERR_INVALID, ORX_ERR_DIM, ORX_ERR_NONFINITE) else OrxError
+        raise cls(rc, last_error())
+
+
+def version() -> str:
+    return lib.orx_version().decode()

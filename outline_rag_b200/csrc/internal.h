@@ -66,5 +66,6 @@ void launch_synth_unit(uint64_t key, uint32_t n_vec, float *dst, cudaStream_t st
 void launch_synth_rows(uint64_t key_noise, uint64_t key_cid, const float *mean, const float *centres,
                        uint32_t n_centres, uint64_t row_start, uint64_t n_rows, float *dst,
                        cudaStream_t st);
+uint64_t synth_stream_key(uint64_t seed, uint64_t tag);
 
 }  // namespace orx

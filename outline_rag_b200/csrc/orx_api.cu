@@ -151,6 +151,8 @@ struct orx_index {
     PinBuf<int> h_flag;
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> scan_ev;   // pairs bracketing each scan launch of the current search
+    size_t scan_ev_used = 0;
     orx::UmmaPlan *umma = nullptr;
     mutable std::mutex mu;
     orx_stats stats{};
@@ -222,6 +224,30 @@ int grow_table(orx_index *ix, uint64_t need) {
 }
 
 // ---------------------------------------------------------------- search core
+// a fresh event from the per-search pool (pairs: before / after one scan launch)
+cudaEvent_t scan_event(orx_index *ix) {
+    if (ix->scan_ev_used == ix->scan_ev.size()) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
+        ix->scan_ev.push_back(e);
+    }
+    return ix->scan_ev[ix->scan_ev_used++];
+}
+void harvest_scan_events(orx_index *ix) {       // stream is synchronised
+    float last = 0.f;
+    for (size_t i = 0; i + 1 < ix->scan_ev_used; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ix->scan_ev[i], ix->scan_ev[i + 1]) == cudaSuccess) {
+            ix->stats.scan_ms_total += ms;
+            ix->stats.scan_launches += 1;
+            last += ms;
+        }
+    }
+    if (ix->scan_ev_used) ix->stats.last_scan_ms = last;
+    ix->scan_ev_used = 0;
+    cudaGetLastError();
+}
+
 struct SearchOut {          // where the results of query j go (device pointers)
     orx_id *ids;
     double *dist;
@@ -264,8 +290,11 @@ int gemv_pass(orx_index *ix, int q0, int nq, int k, const SearchOut &out, int *f
         const int m = std::min(GEMV_QCHUNK, nq - s);
         const int qa = q0 + s;
         CK(ix->partial.ensure((size_t)m * grid * 32 * slots));
+        cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
+        if (e0 && e1) CK(cudaEventRecord(e0, ix->stream));
         orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qa * ORX_DIM, m,
                               slots, ix->partial.p, grid, ix->stream);
+        if (e0 && e1) CK(cudaEventRecord(e1, ix->stream));
         orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, ix->q_dev.p + (size_t)qa * ORX_DIM,
                              ix->prep.p + qa, ix->partial.p, grid, slots, m, k, n_rows, eps,
                              out.ids + (size_t)qa * k, out.dist + (size_t)qa * k, out.counts + qa,
@@ -284,6 +313,7 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
     cudaStream_t st = ix->stream;
     const size_t nk = (size_t)nq * k;
+    ix->scan_ev_used = 0;
 
     CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
     CK(ix->qhat.ensure((size_t)nq * ORX_DIM));
@@ -390,7 +420,7 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
     }
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ix->ev[1], ix->ev[2]) == cudaSuccess) ix->stats.last_scan_ms = ms;
+    harvest_scan_events(ix);
     if (cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]) == cudaSuccess) ix->stats.last_search_ms = ms;
     cudaGetLastError();
     ix->stats.last_path = path;
@@ -470,6 +500,7 @@ void orx_destroy(orx_index *ix) {
     ix->d_flag.release(); ix->h_u32a.release(); ix->h_u32b.release(); ix->h_flag.release();
     for (auto &e : ix->ev)
         if (e) cudaEventDestroy(e);
+    for (auto &e : ix->scan_ev) cudaEventDestroy(e);
     cudaGetLastError();
     delete ix;
 }
@@ -750,8 +781,6 @@ struct SynthState {
 std::mutex g_synth_mu;
 std::map<std::tuple<int, uint64_t, uint32_t>, SynthState> g_synth;
 }  // namespace
-
-namespace orx { uint64_t synth_stream_key(uint64_t seed, uint64_t tag); }
 
 int orx_synth_rows(int device, void *cuda_stream, uint64_t seed, uint32_t n_centres, uint64_t row_start,
                    uint64_t n_rows, float *dst_device) {

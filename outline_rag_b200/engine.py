@@ -1,0 +1,236 @@
+"""`Index`: the Python face of one device-resident embedding table (one GPU).
+
+Thin wrapper over the C-ABI (`include/orx.h`) -- every method is one `orx_*` call; no
+arithmetic happens in Python.  PyTorch is used only for tensor hand-off (device pointers,
+current stream).  Ids are 128-bit (``langchain_id UUID``, reference app/database.py:119)
+carried as ``uint64 [n, 2]`` (hi, lo) arrays; helpers convert UUID strings / ints.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import uuid
+from typing import Iterable, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import DTYPE_BF16, DTYPE_F32, ORX_DIM, OrxError, OrxId, OrxStats, check, lib
+
+try:  # tensor hand-off only
+    import torch
+except Exception:  # pragma: no cover - torch is part of the image
+    torch = None
+
+_DTYPES = {"fp32": DTYPE_F32, "f32": DTYPE_F32, "float32": DTYPE_F32,
+           "bf16": DTYPE_BF16, "bfloat16": DTYPE_BF16, DTYPE_F32: DTYPE_F32, DTYPE_BF16: DTYPE_BF16}
+
+
+# ----------------------------------------------------------------------------- ids
+def ids_to_array(ids) -> np.ndarray:
+    """Anything id-like -> contiguous ``uint64 [n, 2]`` (hi, lo).
+
+    Accepts a ``uint64 [n, 2]`` array, a 1-D integer array (ids < 2**64), or a sequence of
+    ``int`` / ``uuid.UUID`` / UUID strings (what ``adelete(ids=[...])`` receives,
+    reference app/rag.py:231)."""
+    if isinstance(ids, np.ndarray):
+        if ids.ndim == 2 and ids.shape[1] == 2:
+            return np.ascontiguousarray(ids, dtype=np.uint64)
+        if ids.ndim == 1 and ids.dtype.kind in "iu":
+            out = np.zeros((ids.shape[0], 2), np.uint64)
+            out[:, 1] = ids.astype(np.uint64)
+            return out
+    ids = list(ids)
+    out = np.empty((len(ids), 2), np.uint64)
+    for i, v in enumerate(ids):
+        if isinstance(v, str):
+            v = uuid.UUID(v).int
+        elif isinstance(v, uuid.UUID):
+            v = v.int
+        else:
+            v = int(v)
+        if v < 0 or v >> 128:
+            raise ValueError(f"id {v} does not fit 128 bits")
+        out[i, 0] = v >> 64
+        out[i, 1] = v & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def ids_to_ints(ids: np.ndarray) -> list[int]:
+    a = np.asarray(ids, dtype=np.uint64).reshape(-1, 2)
+    return [(int(h) << 64) | int(l) for h, l in a]
+
+
+def ids_to_uuid_strs(ids: np.ndarray) -> list[str]:
+    return [str(uuid.UUID(int=v)) for v in ids_to_ints(ids)]
+
+
+def _is_cuda_tensor(x) -> bool:
+    return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def _host_f32(x, what: str) -> np.ndarray:
+    if torch is not None and isinstance(x, torch.Tensor):
+        x = x.detach().cpu().numpy()
+    a = np.asarray(x)
+    if a.ndim == 1:
+        a = a.reshape(1, -1)
+    if a.ndim != 2:
+        raise _lib.OrxValueError(_lib.ORX_ERR_DIM, f"{what} must be [n, {ORX_DIM}]")
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+class Index:
+    """One GPU's share of ``langchain_pg_embedding.embedding`` (reference app/database.py:118-131).
+
+    ``dtype``: ``"fp32"`` keeps rows verbatim (bit-exact ids vs the oracle), ``"bf16"`` stores
+    RNE-bf16 of the normalised row (half the HBM traffic; recall@k is reported)."""
+
+    def __init__(self, dtype="fp32", capacity: int = 0, device: int | None = None, dim: int = ORX_DIM):
+        if device is None:
+            device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+        self._h = C.c_void_p()
+        self.device = int(device)
+        check(lib.orx_create(C.byref(self._h), int(dim), _DTYPES[dtype], int(capacity), self.device))
+        self.dtype = "fp32" if _DTYPES[dtype] == DTYPE_F32 else "bf16"
+
+    # -- lifetime
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            lib.orx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):  # noqa: D401
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __len__(self) -> int:
+        return int(lib.orx_size(self._h))
+
+    @property
+    def capacity(self) -> int:
+        return int(lib.orx_capacity(self._h))
+
+    def use_torch_stream(self) -> None:
+        """Launch on torch's current stream so ``torch.cuda.Event`` timing sees the kernels."""
+        check(lib.orx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        check(lib.orx_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def stats(self) -> dict:
+        st = OrxStats()
+        check(lib.orx_get_stats(self._h, C.byref(st)))
+        return {name: getattr(st, name) for name, _ in OrxStats._fields_ if name != "reserved"}
+
+    # -- writes
+    def upsert(self, ids, vecs) -> None:
+        """``aadd_documents`` -> INSERT ... ON CONFLICT DO UPDATE (reference app/rag.py:235)."""
+        ida = ids_to_array(ids)
+        if _is_cuda_tensor(vecs):
+            if vecs.dim() != 2 or vecs.dtype != torch.float32:
+                raise _lib.OrxValueError(_lib.ORX_ERR_DIM, "device vecs must be a float32 [n, dim] tensor")
+            v = vecs.contiguous()
+            n, dim, ptr = v.shape[0], v.shape[1], v.data_ptr()
+        else:
+            v = _host_f32(vecs, "vecs")
+            n, dim, ptr = v.shape[0], v.shape[1], v.ctypes.data
+        if ida.shape[0] != n:
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, f"{ida.shape[0]} ids for {n} vectors")
+        check(lib.orx_upsert(self._h, C.c_void_p(ida.ctypes.data), C.c_void_p(ptr), n, dim))
+
+    def delete(self, ids) -> int:
+        """``adelete(ids=[...])`` -> DELETE ... WHERE langchain_id IN (...) (reference app/rag.py:231)."""
+        ida = ids_to_array(ids)
+        removed = C.c_uint64(0)
+        check(lib.orx_delete(self._h, C.c_void_p(ida.ctypes.data), ida.shape[0], C.byref(removed)))
+        return int(removed.value)
+
+    def contains(self, one_id) -> bool:
+        a = ids_to_array([one_id])
+        return bool(lib.orx_contains(self._h, OrxId(int(a[0, 0]), int(a[0, 1]))))
+
+    def fetch(self, ids):
+        """Stored rows as fp32 ``[n, dim]`` + found mask (debugging / snapshots)."""
+        ida = ids_to_array(ids)
+        n = ida.shape[0]
+        out = np.zeros((n, ORX_DIM), np.float32)
+        found = np.zeros(n, np.int32)
+        check(lib.orx_fetch(self._h, C.c_void_p(ida.ctypes.data), n, C.c_void_p(out.ctypes.data),
+                            C.c_void_p(found.ctypes.data)))
+        return out, found.astype(bool)
+
+    # -- reads
+    def search(self, queries, k: int = 12):
+        """Exact ``ORDER BY embedding <=> :q LIMIT :k`` for each query row.
+
+        Host input (NumPy / CPU tensor) -> NumPy ``(ids uint64 [nq,k,2], dist float64 [nq,k],
+        counts int32 [nq])``.  CUDA tensor input -> the same as device tensors (ids int64 bit
+        patterns), no host copies of the results."""
+        if _is_cuda_tensor(queries):
+            q = queries.contiguous()
+            if q.dim() == 1:
+                q = q.unsqueeze(0)
+            if q.dtype != torch.float32:
+                raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "device queries must be float32")
+            nq, dim = q.shape
+            ids = torch.empty((nq, k, 2), dtype=torch.int64, device=q.device)
+            dist = torch.empty((nq, k), dtype=torch.float64, device=q.device)
+            cnt = torch.empty((nq,), dtype=torch.int32, device=q.device)
+            check(lib.orx_search(self._h, C.c_void_p(q.data_ptr()), nq, dim, int(k), C.c_void_p(ids.data_ptr()),
+                                 C.c_void_p(dist.data_ptr()), C.c_void_p(cnt.data_ptr())))
+            return ids, dist, cnt
+        q = _host_f32(queries, "queries")
+        nq, dim = q.shape
+        ids = np.zeros((nq, max(k, 0), 2), np.uint64)
+        dist = np.full((nq, max(k, 0)), np.nan, np.float64)
+        cnt = np.zeros(nq, np.int32)
+        check(lib.orx_search(self._h, C.c_void_p(q.ctypes.data), nq, dim, int(k), C.c_void_p(ids.ctypes.data),
+                             C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
+        return ids, dist, cnt
+
+    def merge_topk(self, ids, dist, counts, k: int):
+        """Merge ``[n_lists, nq, k]`` shard results (NumPy or CUDA tensors) into the global top-k."""
+        if _is_cuda_tensor(ids):
+            n_lists, nq = ids.shape[0], ids.shape[1]
+            oi = torch.empty((nq, k, 2), dtype=torch.int64, device=ids.device)
+            od = torch.empty((nq, k), dtype=torch.float64, device=ids.device)
+            oc = torch.empty((nq,), dtype=torch.int32, device=ids.device)
+            check(lib.orx_merge_topk(self._h, n_lists, nq, int(k), C.c_void_p(ids.contiguous().data_ptr()),
+                                     C.c_void_p(dist.contiguous().data_ptr()),
+                                     C.c_void_p(counts.contiguous().data_ptr()), C.c_void_p(oi.data_ptr()),
+                                     C.c_void_p(od.data_ptr()), C.c_void_p(oc.data_ptr())))
+            return oi, od, oc
+        ids = np.ascontiguousarray(ids, np.uint64)
+        dist = np.ascontiguousarray(dist, np.float64)
+        counts = np.ascontiguousarray(counts, np.int32)
+        n_lists, nq = ids.shape[0], ids.shape[1]
+        oi = np.zeros((nq, k, 2), np.uint64)
+        od = np.full((nq, k), np.nan, np.float64)
+        oc = np.zeros(nq, np.int32)
+        check(lib.orx_merge_topk(self._h, n_lists, nq, int(k), C.c_void_p(ids.ctypes.data),
+                                 C.c_void_p(dist.ctypes.data), C.c_void_p(counts.ctypes.data),
+                                 C.c_void_p(oi.ctypes.data), C.c_void_p(od.ctypes.data),
+                                 C.c_void_p(oc.ctypes.data)))
+        return oi, od, oc
+
+
+def synth_rows_device(device: int, seed: int, n_centres: int, row_start: int, n_rows: int, out=None):
+    """Rows ``row_start .. row_start+n_rows-1`` of the synthetic table, generated in HBM
+    (bit-identical to ``synth.Synth.rows``).  Returns a float32 CUDA tensor."""
+    if out is None:
+        out = torch.empty((n_rows, ORX_DIM), dtype=torch.float32, device=f"cuda:{device}")
+    stream = torch.cuda.current_stream(device).cuda_stream
+    check(lib.orx_synth_rows(int(device), C.c_void_p(stream), int(seed), int(n_centres), int(row_start),
+                             int(n_rows), C.c_void_p(out.data_ptr())))
+    return out
+
+
+__all__ = ["Index", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device"]

@@ -1,0 +1,130 @@
+"""Row-sharded table across the GPUs of one NVSwitch box: one process per GPU.
+
+SURVEY.md 8(e): rows are independent, so the table is partitioned by
+``shard = mix64(id) mod G`` (balanced under upsert/delete churn); every rank receives the
+full query batch, scans its shard, and only the k candidates per query are exchanged:
+ONE ``all_gather`` of a packed ``[nq, 3k+1]`` int64 block per rank (144..147 KB at
+k=12), then the on-device merge (``orx_merge_topk``) with the same ordering contract
+(distance ASC, NaN last, id ASC).  Distances are the canonical binary64 values, so shard
+results are comparable bit for bit and the merged answer equals the single-GPU answer.
+
+The local index and the merge are injectable so that the partition / exchange logic is
+covered by world_size-2 ``gloo`` tests on CPU (tests/test_sharded_gloo.py).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .engine import Index, ids_to_array
+
+_GOLD = np.uint64(0x9E3779B97F4A7C15)
+_M1 = np.uint64(0xBF58476D1CE4E5B9)
+_M2 = np.uint64(0x94D049BB133111EB)
+
+
+def shard_of(ids: np.ndarray, world: int) -> np.ndarray:
+    """``mix64(hi * GOLD ^ lo) mod world`` for ``uint64 [n, 2]`` ids -> int64 [n]."""
+    ids = np.asarray(ids, dtype=np.uint64).reshape(-1, 2)
+    with np.errstate(over="ignore"):
+        z = ids[:, 0] * _GOLD ^ ids[:, 1]
+        z = (z ^ (z >> np.uint64(30))) * _M1
+        z = (z ^ (z >> np.uint64(27))) * _M2
+        z = z ^ (z >> np.uint64(31))
+    return (z % np.uint64(world)).astype(np.int64)
+
+
+def pack_results(ids: torch.Tensor, dist_: torch.Tensor, counts: torch.Tensor) -> torch.Tensor:
+    """[nq,k,2] int64 + [nq,k] float64 + [nq] int32 -> one int64 [nq, 3k+1] block (bit copies)."""
+    nq, k = dist_.shape
+    out = torch.empty((nq, 3 * k + 1), dtype=torch.int64, device=ids.device)
+    out[:, :2 * k] = ids.reshape(nq, 2 * k)
+    out[:, 2 * k:3 * k] = dist_.view(torch.int64)
+    out[:, 3 * k] = counts.to(torch.int64)
+    return out
+
+
+def unpack_results(block: torch.Tensor, k: int):
+    """inverse of :func:`pack_results` for a ``[..., nq, 3k+1]`` block."""
+    ids = block[..., :2 * k].contiguous().reshape(*block.shape[:-1], k, 2)
+    dist_ = block[..., 2 * k:3 * k].contiguous().view(torch.float64)
+    counts = block[..., 3 * k].to(torch.int32).contiguous()
+    return ids, dist_, counts
+
+
+class ShardedIndex:
+    """The table of one rank + the exchange step.  All ranks must call every method
+    collectively with the same arguments (upsert/delete take the FULL batch and keep only
+    the rows this rank owns, so no data-path collective is needed on the write side)."""
+
+    def __init__(self, dtype: str = "fp32", capacity_per_rank: int = 0, device: Optional[int] = None,
+                 group=None, local_index=None, merge_fn: Optional[Callable] = None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.local = local_index if local_index is not None else Index(dtype, capacity_per_rank, device)
+        self._merge = merge_fn if merge_fn is not None else self.local.merge_topk
+        self.gather_launches = 0
+
+    def __len__(self) -> int:
+        return len(self.local)
+
+    def global_size(self) -> int:
+        n = torch.tensor([len(self.local)], dtype=torch.int64)
+        if self.world > 1:
+            backend = dist.get_backend(self.group)
+            if backend == "nccl":
+                n = n.cuda()
+            dist.all_reduce(n, group=self.group)
+        return int(n.item())
+
+    # ------------------------------------------------------------------ writes
+    def _mine(self, ida: np.ndarray) -> np.ndarray:
+        return np.nonzero(shard_of(ida, self.world) == self.rank)[0]
+
+    def upsert(self, ids, vecs) -> int:
+        ida = ids_to_array(ids)
+        sel = self._mine(ida)
+        if sel.size:
+            v = vecs[torch.as_tensor(sel, device=vecs.device)] if isinstance(vecs, torch.Tensor) \
+                else np.asarray(vecs, np.float32)[sel]
+            self.local.upsert(ida[sel], v)
+        return int(sel.size)
+
+    def upsert_local(self, ids, vecs) -> None:
+        """Rows the caller already knows belong to this rank (bulk load of a pre-partitioned table)."""
+        self.local.upsert(ids, vecs)
+
+    def delete(self, ids) -> int:
+        ida = ids_to_array(ids)
+        sel = self._mine(ida)
+        return self.local.delete(ida[sel]) if sel.size else 0
+
+    # ------------------------------------------------------------------- reads
+    def search(self, queries, k: int = 12):
+        """Global top-k on every rank.  ``queries`` is identical on all ranks (CUDA tensor for the
+        NCCL path; NumPy for the CPU/gloo test path)."""
+        ids, dist_, cnt = self.local.search(queries, k)
+        if self.world == 1:
+            return ids, dist_, cnt
+        as_numpy = not isinstance(ids, torch.Tensor)
+        if as_numpy:
+            ids = torch.from_numpy(np.ascontiguousarray(ids).view(np.int64))
+            dist_ = torch.from_numpy(np.ascontiguousarray(dist_))
+            cnt = torch.from_numpy(np.ascontiguousarray(cnt))
+        block = pack_results(ids, dist_, cnt)
+        nq = block.shape[0]
+        gathered = torch.empty((self.world * nq, block.shape[1]), dtype=torch.int64, device=block.device)
+        dist.all_gather_into_tensor(gathered, block, group=self.group)   # rank-major concatenation
+        gathered = gathered.view(self.world, nq, block.shape[1])
+        self.gather_launches += 1
+        g_ids, g_dist, g_cnt = unpack_results(gathered, k)
+        if as_numpy:
+            return self._merge(g_ids.numpy().view(np.uint64), g_dist.numpy(), g_cnt.numpy(), k)
+        return self._merge(g_ids, g_dist, g_cnt, k)
+
+
+__all__ = ["ShardedIndex", "shard_of", "pack_results", "unpack_results"]

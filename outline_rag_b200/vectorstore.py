@@ -1,0 +1,216 @@
+"""`GpuVectorStore`: the drop-in for the object bound to ``rag.vector_store``.
+
+The reference builds ``AsyncPGVectorStore.create(engine, embedding_service,
+table_name="langchain_pg_embedding", metadata_columns=[...])`` (reference app/rag.py:69-79)
+and uses exactly five things on it:
+
+* ``.as_retriever(search_kwargs={"k": TOP_K})``            rag.py:85-87  (-> ``asimilarity_search``)
+* ``await .adelete(ids=[uuid, ...])``                       rag.py:231, :371
+* ``await .aadd_documents(chunks)``                         rag.py:235
+* (implied) ``asimilarity_search_with_score_by_vector(embedding, k)`` -> ``[(Document, distance)]``
+
+This class keeps those names, argument meanings, return shapes and error behaviour
+(exceptions propagate; api.py:125-127 turns them into "no documents").  The similarity
+arithmetic + ORDER BY ... LIMIT k run on the B200 through the C-ABI; document text and the
+four metadata columns stay in a `DocStore` (Postgres in production -- see INTEGRATION.md;
+an in-memory dict here and in tests) and are hydrated by id in rank order.
+
+Blocking C calls run in ``asyncio.to_thread`` so the uvicorn event loop is never stalled.
+"""
+from __future__ import annotations
+
+import asyncio
+import uuid
+from dataclasses import dataclass, field
+from typing import Any, Iterable, Optional, Sequence
+
+import numpy as np
+
+from .engine import Index, ids_to_array, ids_to_uuid_strs
+
+try:  # use the real class when the host application has langchain installed
+    from langchain_core.documents import Document  # type: ignore
+except Exception:
+    @dataclass
+    class Document:  # same three fields `rag.py` / `api.py` touch
+        page_content: str
+        metadata: dict = field(default_factory=dict)
+        id: Optional[str] = None
+
+
+DEFAULT_METADATA_COLUMNS = ["source_id", "title", "outline_updated_at_str", "url"]   # rag.py:73-78
+
+
+class MemoryDocStore:
+    """``langchain_id -> (content, metadata)``: what stays in Postgres in production
+    (columns ``content`` + the 4 metadata columns, reference app/database.py:118-131)."""
+
+    def __init__(self):
+        self._rows: dict[str, tuple[str, dict]] = {}
+
+    def put_many(self, ids: Sequence[str], contents: Sequence[str], metadatas: Sequence[dict]) -> None:
+        for i, c, m in zip(ids, contents, metadatas):
+            self._rows[i] = (c, dict(m))
+
+    def get_many(self, ids: Sequence[str]) -> list[Optional[tuple[str, dict]]]:
+        return [self._rows.get(i) for i in ids]
+
+    def delete_many(self, ids: Iterable[str]) -> None:
+        for i in ids:
+            self._rows.pop(i, None)
+
+    def ids_for_source(self, source_ids: Iterable[str]) -> list[str]:
+        """``SELECT langchain_id ... WHERE source_id = ANY(:ids)`` (reference app/rag.py:216-224)."""
+        want = set(source_ids)
+        return [i for i, (_, m) in self._rows.items() if m.get("source_id") in want]
+
+
+def _canon_uuid(v) -> str:
+    if isinstance(v, uuid.UUID):
+        return str(v)
+    if isinstance(v, int):
+        return str(uuid.UUID(int=v))
+    return str(uuid.UUID(str(v)))
+
+
+class GpuRetriever:
+    """``VectorStoreRetriever`` stand-in (search_type="similarity")."""
+
+    def __init__(self, store: "GpuVectorStore", search_kwargs: Optional[dict] = None):
+        self.vectorstore = store
+        self.search_kwargs = dict(search_kwargs or {})
+
+    async def ainvoke(self, query: str, **_: Any) -> list:
+        return await self.vectorstore.asimilarity_search(query, **self.search_kwargs)
+
+    def invoke(self, query: str, **_: Any) -> list:
+        return self.vectorstore.similarity_search(query, **self.search_kwargs)
+
+
+class GpuVectorStore:
+    def __init__(self, index: Index, embedding_service, doc_store=None,
+                 metadata_columns: Optional[list[str]] = None, table_name: str = "langchain_pg_embedding"):
+        self.index = index
+        self.embedding_service = embedding_service
+        self.doc_store = doc_store if doc_store is not None else MemoryDocStore()
+        self.metadata_columns = list(metadata_columns or DEFAULT_METADATA_COLUMNS)
+        self.table_name = table_name
+
+    # ---------------------------------------------------------------- construction
+    @classmethod
+    async def create(cls, engine=None, embedding_service=None, table_name: str = "langchain_pg_embedding",
+                     metadata_columns: Optional[list[str]] = None, *, dtype: str = "fp32", capacity: int = 0,
+                     device: Optional[int] = None, doc_store=None, **_: Any) -> "GpuVectorStore":
+        """Same call shape as ``AsyncPGVectorStore.create`` (reference app/rag.py:69-79).
+        ``engine`` (the PGEngine) is accepted and handed to the doc store factory if it is
+        callable; the vector column itself now lives in HBM."""
+        if embedding_service is None:
+            raise ValueError("embedding_service is required")
+        if callable(doc_store):
+            doc_store = doc_store(engine)
+        index = await asyncio.to_thread(Index, dtype, capacity, device)
+        return cls(index, embedding_service, doc_store, metadata_columns, table_name)
+
+    @classmethod
+    def create_sync(cls, embedding_service, **kw) -> "GpuVectorStore":
+        doc_store = kw.pop("doc_store", None)
+        index = Index(kw.pop("dtype", "fp32"), kw.pop("capacity", 0), kw.pop("device", None))
+        return cls(index, embedding_service, doc_store, kw.pop("metadata_columns", None),
+                   kw.pop("table_name", "langchain_pg_embedding"))
+
+    def as_retriever(self, search_kwargs: Optional[dict] = None, **_: Any) -> GpuRetriever:
+        return GpuRetriever(self, search_kwargs)
+
+    # ---------------------------------------------------------------- writes
+    def add_embeddings(self, texts: Sequence[str], embeddings, metadatas: Optional[Sequence[dict]] = None,
+                       ids: Optional[Sequence] = None) -> list[str]:
+        n = len(texts)
+        if ids is None:
+            ids = [None] * n
+        ids = [_canon_uuid(i) if i is not None else str(uuid.uuid4()) for i in ids]   # `doc.id or uuid4()`
+        metadatas = list(metadatas) if metadatas is not None else [{} for _ in range(n)]
+        emb = np.asarray(embeddings, dtype=np.float32)
+        if n == 0:
+            return []
+        self.index.upsert(ids, emb)                      # raises on wrong dim / NaN, nothing stored
+        self.doc_store.put_many(ids, list(texts), metadatas)
+        return ids
+
+    async def aadd_embeddings(self, texts, embeddings, metadatas=None, ids=None) -> list[str]:
+        return await asyncio.to_thread(self.add_embeddings, texts, embeddings, metadatas, ids)
+
+    async def aadd_documents(self, documents: Sequence, ids: Optional[Sequence] = None, **_: Any) -> list[str]:
+        """reference app/rag.py:235.  ids default to ``doc.id or uuid4()``; texts are embedded with
+        ``embedding_service.aembed_documents`` (remote bge-m3 in the reference)."""
+        texts = [d.page_content for d in documents]
+        metas = [dict(getattr(d, "metadata", {}) or {}) for d in documents]
+        if ids is None:
+            ids = [getattr(d, "id", None) for d in documents]
+        if not texts:
+            return []
+        emb = await self.embedding_service.aembed_documents(texts)
+        return await self.aadd_embeddings(texts, emb, metas, ids)
+
+    def add_documents(self, documents: Sequence, ids: Optional[Sequence] = None) -> list[str]:
+        texts = [d.page_content for d in documents]
+        metas = [dict(getattr(d, "metadata", {}) or {}) for d in documents]
+        if ids is None:
+            ids = [getattr(d, "id", None) for d in documents]
+        if not texts:
+            return []
+        return self.add_embeddings(texts, self.embedding_service.embed_documents(texts), metas, ids)
+
+    def delete(self, ids: Optional[Sequence] = None, **_: Any) -> bool:
+        """reference app/rag.py:231, :371.  Unknown ids are ignored (SQL DELETE semantics)."""
+        if not ids:
+            return False
+        sids = [_canon_uuid(i) for i in ids]
+        self.index.delete(sids)
+        self.doc_store.delete_many(sids)
+        return True
+
+    async def adelete(self, ids: Optional[Sequence] = None, **kw: Any) -> bool:
+        return await asyncio.to_thread(self.delete, ids, **kw)
+
+    # ---------------------------------------------------------------- reads
+    def _hydrate(self, ids_row: np.ndarray, dist_row: np.ndarray, count: int) -> list[tuple[Any, float]]:
+        sids = ids_to_uuid_strs(ids_row[:count])
+        rows = self.doc_store.get_many(sids)
+        out = []
+        for sid, row, d in zip(sids, rows, dist_row[:count]):
+            content, meta = row if row is not None else ("", {})
+            out.append((Document(page_content=content, metadata=dict(meta), id=sid), float(d)))
+        return out
+
+    def similarity_search_with_score_by_vector(self, embedding, k: int = 4, filter=None, **_: Any):
+        """-> ``[(Document, cosine distance)]`` ascending, exactly the SQL's ORDER BY ... LIMIT k."""
+        if filter is not None:
+            raise NotImplementedError("metadata filters are not pushed into the scan yet (SURVEY.md 8f-4)")
+        ids, dist, cnt = self.index.search(np.asarray(embedding, dtype=np.float32).reshape(1, -1), k)
+        return self._hydrate(ids[0], dist[0], int(cnt[0]))
+
+    def batch_search_by_vector(self, embeddings, k: int = 4):
+        """Many queries in one scan (the micro-batching front end of SURVEY.md 8f-3 calls this)."""
+        ids, dist, cnt = self.index.search(np.asarray(embeddings, dtype=np.float32), k)
+        return [self._hydrate(ids[i], dist[i], int(cnt[i])) for i in range(ids.shape[0])]
+
+    async def asimilarity_search_with_score_by_vector(self, embedding, k: int = 4, filter=None, **kw: Any):
+        return await asyncio.to_thread(self.similarity_search_with_score_by_vector, embedding, k, filter)
+
+    async def asimilarity_search_by_vector(self, embedding, k: int = 4, **kw: Any):
+        return [d for d, _ in await self.asimilarity_search_with_score_by_vector(embedding, k, **kw)]
+
+    async def asimilarity_search_with_score(self, query: str, k: int = 4, **kw: Any):
+        emb = await self.embedding_service.aembed_query(query)
+        return await self.asimilarity_search_with_score_by_vector(emb, k, **kw)
+
+    async def asimilarity_search(self, query: str, k: int = 4, **kw: Any):
+        """What the retriever calls (reference app/rag.py:85-87 via api.py:122): the distance is dropped."""
+        return [d for d, _ in await self.asimilarity_search_with_score(query, k, **kw)]
+
+    def similarity_search(self, query: str, k: int = 4, **kw: Any):
+        emb = self.embedding_service.embed_query(query)
+        return [d for d, _ in self.similarity_search_with_score_by_vector(emb, k, **kw)]
+
+
+__all__ = ["GpuVectorStore", "GpuRetriever", "MemoryDocStore", "Document", "DEFAULT_METADATA_COLUMNS"]

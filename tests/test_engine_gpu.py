@@ -1,0 +1,365 @@
+"""Parity tests proper: the CUDA path through the C-ABI vs the oracle, same seeded inputs.
+
+Bar (BASELINE.json north_star): fp32 mode -> ids bit-exact (ties by chunk id); the canonical
+distance is DEFINED as the fixed-order binary64 evaluation (oracle/cosine_topk.py:canon_distance)
+and the CUDA rescore evaluates the identical tree, so distances are compared BIT FOR BIT too
+(tolerance 0, far inside the 1e-5 relative the north star allows).  bf16 mode -> bit-exact
+against the oracle run on the rows as stored (RNE bf16 of the normalised row) + recall@12 vs fp32.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cosine_topk as O
+from tests._helpers import stored_bf16_rows
+
+pytestmark = pytest.mark.gpu
+DIM, K = 1024, 12
+
+
+def _ids(n, start=0):
+    return O.ids_arange(start, start + n)
+
+
+def _check_exact(index, X, ids, Q, k=K, oracle_rows=None):
+    Xo = X if oracle_rows is None else oracle_rows
+    g_ids, g_d, g_c = index.search(Q, k)
+    for i in range(Q.shape[0]):
+        w_ids, w_d = O.topk_exact(Xo, ids, Q[i], k)
+        m = len(w_d)
+        assert g_c[i] == m
+        assert np.array_equal(g_ids[i, :m], w_ids), f"query {i}: ids differ"
+        assert np.array_equal(g_d[i, :m].view(np.uint64), w_d.view(np.uint64)), f"query {i}: distance bits differ"
+        assert np.isnan(g_d[i, m:]).all() and (g_ids[i, m:] == 0).all()
+    return g_ids, g_d, g_c
+
+
+@pytest.fixture()
+def Index():
+    import outline_rag_b200 as orx
+    return orx.Index
+
+
+# ------------------------------------------------------------------ seeded parity, both dtypes
+def test_fp32_bit_exact_vs_oracle(Index, small_table):
+    X, Q, anchors = small_table
+    ids = _ids(X.shape[0])
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        assert len(ix) == X.shape[0]
+        g_ids, _, _ = _check_exact(ix, X, ids, Q)
+        assert (g_ids[:, 0, 1] == anchors.astype(np.uint64)).all()
+        st = ix.stats()
+        assert st["kernel_launches"] > 0 and st["last_path"] in (1, 2)
+
+
+def test_bf16_bit_exact_vs_oracle_on_stored_rows_and_recall(Index, small_table):
+    X, Q, _ = small_table
+    ids = _ids(X.shape[0])
+    Xb = stored_bf16_rows(X)
+    with Index("bf16") as ix:
+        ix.upsert(ids, X)
+        got, _ = ix.fetch(ids[:64])
+        assert np.array_equal(got.view(np.uint32), Xb[:64].view(np.uint32))
+        g_ids, _, _ = _check_exact(ix, X, ids, Q, oracle_rows=Xb)
+    rec = np.mean([O.recall_at_k(g_ids[i], O.topk_exact(X, ids, Q[i], K)[0]) for i in range(Q.shape[0])])
+    assert rec >= 0.95, rec
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_golden_vectors_through_the_cuda_path(Index, synth100k, dtype):
+    with open(os.path.join(os.path.dirname(__file__), "golden", "topk_golden.json")) as f:
+        G = json.load(f)
+    X = synth100k.table(G["n_rows"])
+    Q, _ = synth100k.queries(len(G["cases"]), G["n_rows"])
+    with Index(dtype) as ix:
+        ix.upsert(_ids(G["n_rows"]), X)
+        g_ids, g_d, g_c = ix.search(Q, G["k"])
+    pre = "" if dtype == "fp32" else "bf16_"
+    for qi, case in enumerate(G["cases"]):
+        assert O.ids_to_ints(g_ids[qi]) == case[pre + "ids"]
+        assert [float(d).hex() for d in g_d[qi]] == case[pre + "dist_hex"]
+
+
+@pytest.mark.parametrize("nq", [1, 2, 5, 33, 64, 130])
+def test_query_batches(Index, small_table, nq):
+    X, Q, _ = small_table
+    ids = _ids(4096)
+    rng = np.random.default_rng(nq)
+    Qb = np.concatenate([Q, rng.standard_normal((max(0, nq - Q.shape[0]), DIM)).astype(np.float32)])[:nq]
+    with Index("fp32") as ix:
+        ix.upsert(ids, X[:4096])
+        _check_exact(ix, X[:4096], ids, Qb)
+
+
+@pytest.mark.parametrize("k", [1, 2, 12, 16, 17, 32])
+def test_all_k(Index, small_table, k):
+    X, Q, _ = small_table
+    ids = _ids(3000)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X[:3000])
+        _check_exact(ix, X[:3000], ids, Q[:6], k=k)
+
+
+@pytest.mark.parametrize("n", [1, 2, 11, 12, 13, 31, 32, 33, 63, 64, 65, 255, 1023, 2049])
+def test_ragged_table_sizes(Index, small_table, n):
+    X, Q, _ = small_table
+    with Index("fp32") as ix:
+        ix.upsert(_ids(n), X[:n])
+        _check_exact(ix, X[:n], _ids(n), Q[:3])
+
+
+# ------------------------------------------------------------------ known answers
+def test_ka1_identity_basis(Index):
+    X = np.eye(DIM, dtype=np.float32)
+    q = np.arange(DIM, 0, -1).astype(np.float32)
+    with Index("fp32") as ix:
+        ix.upsert(_ids(DIM), X)
+        g_ids, g_d, _ = ix.search(q, K)
+    assert O.ids_to_ints(g_ids[0]) == list(range(K))
+    want = 1.0 - (DIM - np.arange(K)) / np.sqrt(np.sum(q.astype(np.float64) ** 2))
+    np.testing.assert_allclose(g_d[0], want, rtol=0, atol=1e-15)
+
+
+def test_ka2_duplicate_rows_order_by_id(Index):
+    rng = np.random.default_rng(1)
+    base = rng.standard_normal((40, DIM)).astype(np.float32)
+    X = np.concatenate([base] * 5)                       # 200 rows, every vector five times
+    idv = rng.permutation(200) + 1000
+    ids = O.ids_from_ints(idv.tolist())
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        _check_exact(ix, X, ids, base[:4], k=12)
+        g_ids, g_d, _ = ix.search(base[7], 5)
+    same = sorted(int(idv[7 + 40 * j]) for j in range(5))
+    assert O.ids_to_ints(g_ids[0]) == same and (g_d[0] == g_d[0][0]).all()
+
+
+def test_ka2b_many_exact_ties_force_the_exhaustive_path(Index):
+    """More identical rows than the candidate list holds: completeness cannot be proven from
+    the list alone, so the threshold-collect fallback must produce the id-ascending answer."""
+    rng = np.random.default_rng(11)
+    v = rng.standard_normal(DIM).astype(np.float32)
+    X = np.concatenate([np.tile(v, (500, 1)), rng.standard_normal((1500, DIM)).astype(np.float32)])
+    idv = rng.permutation(2000) + 7
+    ids = O.ids_from_ints(idv.tolist())
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        g_ids, g_d, g_c = ix.search(v, K)
+        st = ix.stats()
+    assert O.ids_to_ints(g_ids[0]) == sorted(idv[:500].tolist())[:K]
+    assert (g_d[0] == 0.0).all() or np.allclose(g_d[0], 0.0, atol=1e-15)
+    assert st["fallback_exhaustive"] >= 1
+
+
+def test_ka3_row_scale_invariance(Index, small_table):
+    X, Q, _ = small_table
+    X = X[:2000]
+    rng = np.random.default_rng(2)
+    s = (2.0 ** rng.integers(-20, 21, size=2000)).astype(np.float32)
+    ids = _ids(2000)
+    with Index("fp32") as a, Index("fp32") as b:
+        a.upsert(ids, X)
+        b.upsert(ids, X * s[:, None])
+        ra, rb = a.search(Q[:8], K), b.search(Q[:8], K)
+    assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1].view(np.uint64), rb[1].view(np.uint64))
+
+
+def test_ka3b_extreme_magnitudes_are_still_exact(Index, small_table):
+    """Rows whose norm is far outside fp32's comfortable range are never pruned by the fast scan."""
+    X, Q, _ = small_table
+    X = X[:1500].copy()
+    X[5] *= np.float32(1e-30)
+    X[6] *= np.float32(1e30)
+    X[7] *= np.float32(1e-44)       # denormal elements
+    ids = _ids(1500)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        _check_exact(ix, X, ids, np.stack([X[5], X[6], Q[0], Q[1]]) / np.float32(1.0))
+
+
+def test_ka4_antiparallel_row_distance_two(Index):
+    rng = np.random.default_rng(3)
+    q = rng.standard_normal(DIM).astype(np.float32)
+    X = np.stack([q, -q, 4 * q])
+    with Index("fp32") as ix:
+        ix.upsert(_ids(3), X)
+        g_ids, g_d, g_c = ix.search(q, K)
+    assert g_c[0] == 3 and O.ids_to_ints(g_ids[0, :3]) == [0, 2, 1]
+    assert g_d[0, 0] == 0.0 and g_d[0, 1] == 0.0 and g_d[0, 2] == 2.0
+
+
+def test_ka5_zero_norm_rows_sort_last(Index, small_table):
+    X, Q, _ = small_table
+    X = X[:40].copy()
+    X[[3, 17]] = 0.0
+    ids = _ids(40)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        g_ids, g_d, g_c = ix.search(Q[0], 32)
+        assert g_c[0] == 32 and not np.isnan(g_d[0]).any()           # 38 finite rows >= 32
+        ix.delete(ids[20:])
+        _check_exact(ix, X[:20], ids[:20], Q[:2], k=32)              # 18 finite + 2 NaN rows, NaN last by id
+        g_ids, g_d, g_c = ix.search(Q[0], 32)
+    assert g_c[0] == 20 and np.isnan(g_d[0, 18:20]).all() and O.ids_to_ints(g_ids[0, 18:20]) == [3, 17]
+
+
+def test_zero_query_gives_all_nan_by_id(Index, small_table):
+    X, _, _ = small_table
+    ids = _ids(100)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X[:100])
+        g_ids, g_d, g_c = ix.search(np.zeros(DIM, np.float32), K)
+    assert g_c[0] == K and np.isnan(g_d[0]).all() and O.ids_to_ints(g_ids[0]) == list(range(K))
+
+
+def test_ka6_k_larger_than_table_and_empty_table(Index, small_table):
+    X, Q, _ = small_table
+    with Index("fp32") as ix:
+        g_ids, g_d, g_c = ix.search(Q[:2], K)
+        assert (g_c == 0).all() and np.isnan(g_d).all()
+        ix.upsert(_ids(7), X[:7])
+        _check_exact(ix, X[:7], _ids(7), Q[:2])
+
+
+def test_ka7_delete_and_upsert_semantics(Index, small_table):
+    X, Q, _ = small_table
+    n = 3000
+    ids = _ids(n)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X[:n])
+        top = ix.search(Q[0], K)[0][0]
+        assert ix.delete(top[:5]) == 5
+        assert ix.delete(top[:5]) == 0                     # unknown ids are ignored, like SQL DELETE
+        assert len(ix) == n - 5 and not ix.contains(int(top[0, 1]))
+        keep = np.ones(n, bool)
+        keep[top[:5, 1].astype(np.int64)] = False
+        _check_exact(ix, X[:n][keep], ids[keep], Q[:4])
+        # upsert of an existing id replaces the row in place; size unchanged
+        victim = int(top[7, 1])
+        ix.upsert([victim], X[n + 1][None])
+        assert len(ix) == n - 5
+        Xm = X[:n].copy()
+        Xm[victim] = X[n + 1]
+        _check_exact(ix, Xm[keep], ids[keep], np.stack([Q[0], X[n + 1]]))
+        # the same id twice in one batch: last occurrence wins
+        ix.upsert([victim, victim], np.stack([X[n + 2], X[n + 3]]))
+        Xm[victim] = X[n + 3]
+        _check_exact(ix, Xm[keep], ids[keep], np.stack([X[n + 2], X[n + 3]]))
+        assert ix.stats()["rows_moved"] > 0
+
+
+def test_delete_everything_then_refill(Index, small_table):
+    X, Q, _ = small_table
+    ids = _ids(500)
+    with Index("fp32", capacity=16) as ix:          # also exercises table growth
+        ix.upsert(ids, X[:500])
+        assert ix.capacity >= 500
+        assert ix.delete(ids) == 500 and len(ix) == 0
+        assert ix.search(Q[0], K)[2][0] == 0
+        ix.upsert(ids[:100], X[100:200])
+        _check_exact(ix, X[100:200], ids[:100], Q[:2])
+
+
+def test_ka8_input_errors(Index, small_table):
+    import outline_rag_b200 as orx
+    X, Q, _ = small_table
+    with Index("fp32") as ix:
+        ix.upsert(_ids(10), X[:10])
+        with pytest.raises(orx.OrxValueError, match="dimensions"):
+            ix.upsert(_ids(2), np.zeros((2, 768), np.float32))
+        bad = X[:3].copy()
+        bad[1, 5] = np.nan
+        with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
+            ix.upsert(_ids(3, 100), bad)
+        assert len(ix) == 10                                  # whole batch rejected, table unchanged
+        bad[1, 5] = np.inf
+        with pytest.raises(orx.OrxValueError):
+            ix.upsert(_ids(3, 100), bad)
+        with pytest.raises(orx.OrxValueError, match="dimensions"):
+            ix.search(np.zeros((1, 512), np.float32), K)
+        qbad = Q[:2].copy()
+        qbad[1, 0] = np.nan
+        with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
+            ix.search(qbad, K)
+        for k in (0, 33, -1):
+            with pytest.raises(orx.OrxValueError):
+                ix.search(Q[:1], k)
+        _check_exact(ix, X[:10], _ids(10), Q[:2])             # still healthy afterwards
+
+
+def test_128_bit_ids_and_uuid_order(Index, small_table):
+    import uuid
+    X, Q, _ = small_table
+    rng = np.random.default_rng(9)
+    vals = [int(rng.integers(0, 2**63)) << 64 | int(rng.integers(0, 2**63)) for _ in range(300)]
+    vals[10] = (1 << 127) | 5                                  # top bit set: unsigned order matters
+    ids = O.ids_from_ints(vals)
+    Xd = np.concatenate([X[:150], X[:150]])                    # duplicates across different high words
+    with Index("fp32") as ix:
+        ix.upsert([str(uuid.UUID(int=v)) for v in vals], Xd)
+        _check_exact(ix, Xd, ids, Q[:4])
+        assert ix.contains(str(uuid.UUID(int=vals[10])))
+
+
+# ------------------------------------------------------------------ device hand-off + merge
+def test_device_pointers_in_and_out(Index, small_table):
+    import torch
+    X, Q, _ = small_table
+    ids = _ids(2048)
+    with Index("fp32") as ix:
+        ix.use_torch_stream()
+        ix.upsert(ids, torch.from_numpy(X[:2048]).cuda())
+        h = ix.search(Q[:5], K)
+        d = ix.search(torch.from_numpy(Q[:5]).cuda(), K)
+        assert d[0].is_cuda
+        assert np.array_equal(d[0].cpu().numpy().view(np.uint64), h[0])
+        assert np.array_equal(d[1].cpu().numpy().view(np.uint64), h[1].view(np.uint64))
+        assert np.array_equal(d[2].cpu().numpy(), h[2])
+
+
+@pytest.mark.parametrize("n_shards", [2, 4, 8])
+def test_shard_merge_equals_single_table(Index, small_table, n_shards):
+    """The multi-GPU path emulated on one GPU: G row shards (same partition function as
+    sharded.py), G local searches, orx_merge_topk == the single-table answer, bit for bit."""
+    import torch
+    from outline_rag_b200.sharded import shard_of
+    X, Q, _ = small_table
+    n = 6000
+    ids = _ids(n)
+    owner = shard_of(ids, n_shards)
+    shards = [Index("fp32") for _ in range(n_shards)]
+    try:
+        for s, ix in enumerate(shards):
+            ix.upsert(ids[owner == s], X[:n][owner == s])
+        parts = [ix.search(Q[:9], K) for ix in shards]
+        g_ids = np.stack([p[0] for p in parts])
+        g_d = np.stack([p[1] for p in parts])
+        g_c = np.stack([p[2] for p in parts])
+        m_ids, m_d, m_c = shards[0].merge_topk(g_ids, g_d, g_c, K)
+        dm = shards[0].merge_topk(torch.from_numpy(g_ids.view(np.int64)).cuda(), torch.from_numpy(g_d).cuda(),
+                                  torch.from_numpy(g_c).cuda(), K)
+    finally:
+        for ix in shards:
+            ix.close()
+    for i in range(9):
+        w_ids, w_d = O.topk_exact(X[:n], ids, Q[i], K)
+        assert np.array_equal(m_ids[i], w_ids) and np.array_equal(m_d[i].view(np.uint64), w_d.view(np.uint64))
+    assert np.array_equal(dm[0].cpu().numpy().view(np.uint64), m_ids)
+    assert (m_c == K).all()
+
+
+def test_merge_handles_short_lists(Index, small_table):
+    X, Q, _ = small_table
+    with Index("fp32") as a, Index("fp32") as b:
+        a.upsert(_ids(5), X[:5])
+        b.upsert(_ids(3, 100), X[5:8])
+        pa, pb = a.search(Q[:2], K), b.search(Q[:2], K)
+        m = a.merge_topk(np.stack([pa[0], pb[0]]), np.stack([pa[1], pb[1]]), np.stack([pa[2], pb[2]]), K)
+    allids = np.concatenate([_ids(5), _ids(3, 100)])
+    for i in range(2):
+        w_ids, w_d = O.topk_exact(X[:8], allids, Q[i], K)
+        assert m[2][i] == 8 and np.array_equal(m[0][i, :8], w_ids)
+        assert np.array_equal(m[1][i, :8].view(np.uint64), w_d.view(np.uint64))

@@ -1,0 +1,183 @@
+"""Pins the oracle (oracle/cosine_topk.py, oracle/pgv_cosine.c).
+
+The reference holds no tests, fixtures or golden vectors for this path (SURVEY.md 4 / 8c:
+"parity unpinned"), so the pins are the eight known-answer constructions derived from the SQL
+semantics of `ORDER BY embedding <=> :q LIMIT :k` (reference app/rag.py:85-87) and pgvector's
+published `cosine_distance`, plus the committed golden vectors in tests/golden/.
+"""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cosine_topk as O
+
+DIM = 1024
+K = 12
+
+
+def _ids(n, start=0):
+    return O.ids_arange(start, start + n)
+
+
+# ---------------------------------------------------------------- known answers
+def test_ka1_identity_basis():
+    X = np.eye(DIM, dtype=np.float32)
+    q = np.arange(DIM, 0, -1).astype(np.float32)
+    ids, dist = O.topk_exact(X, _ids(DIM), q, K, exhaustive=True)
+    assert O.ids_to_ints(ids) == list(range(K))
+    want = 1.0 - (DIM - np.arange(K)) / np.sqrt(np.sum(q.astype(np.float64) ** 2))
+    np.testing.assert_allclose(dist, want, rtol=0, atol=1e-15)
+
+
+def test_ka2_duplicates_order_by_id():
+    rng = np.random.default_rng(1)
+    base = rng.standard_normal((4, DIM)).astype(np.float32)
+    X = np.concatenate([base, base, base])          # every row three times
+    ids = O.ids_from_ints([50, 40, 30, 20, 11, 12, 13, 14, 5, 6, 7, 8])
+    got, dist = O.topk_exact(X, ids, base[0], 3, exhaustive=True)
+    assert O.ids_to_ints(got) == [5, 11, 50]         # same row: ids ascending
+    assert dist[0] == dist[1] == dist[2]
+
+
+def test_ka3_scale_invariance():
+    rng = np.random.default_rng(2)
+    X = rng.standard_normal((300, DIM)).astype(np.float32)
+    q = rng.standard_normal(DIM).astype(np.float32)
+    s = (2.0 ** rng.integers(-6, 7, size=300)).astype(np.float32)   # exact power-of-two scalings
+    a_ids, a_d = O.topk_exact(X, _ids(300), q, K, exhaustive=True)
+    b_ids, b_d = O.topk_exact(X * s[:, None], _ids(300), q, K, exhaustive=True)
+    assert np.array_equal(a_ids, b_ids)
+    np.testing.assert_array_equal(a_d, b_d)          # power-of-two scaling is exact in binary64 too
+
+
+def test_ka4_antiparallel_is_two_and_clamped():
+    rng = np.random.default_rng(3)
+    q = rng.standard_normal(DIM).astype(np.float32)
+    X = np.stack([q, -q, 4 * q])     # power-of-two scaling is exact
+    d = O.canon_distance(X, q)
+    assert d[0] == 0.0 and d[2] == 0.0 and d[1] == 2.0
+    assert (d >= 0.0).all() and (d <= 2.0).all()
+
+
+def test_ka5_zero_norm_row_sorts_last():
+    rng = np.random.default_rng(4)
+    X = rng.standard_normal((5, DIM)).astype(np.float32)
+    X[1] = 0.0
+    q = rng.standard_normal(DIM).astype(np.float32)
+    ids, dist = O.topk_exact(X, _ids(5), q, 12, exhaustive=True)
+    assert len(dist) == 5 and np.isnan(dist[-1]) and not np.isnan(dist[:-1]).any()
+    assert O.ids_to_ints(ids)[-1] == 1
+    ids4, dist4 = O.topk_exact(X, _ids(5), q, 4, exhaustive=True)
+    assert 1 not in O.ids_to_ints(ids4)              # returned only when N_live < k
+
+
+def test_ka6_k_larger_than_table():
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((7, DIM)).astype(np.float32)
+    ids, dist = O.topk_exact(X, _ids(7), X[3], 12)
+    assert len(dist) == 7 and O.ids_to_ints(ids)[0] == 3
+    assert (np.diff(dist) >= 0).all()
+    e_ids, e_d = O.topk_exact(X[:0], _ids(0), X[3], 12)
+    assert e_ids.shape == (0, 2) and e_d.shape == (0,)
+
+
+def test_ka8_input_validation():
+    with pytest.raises(ValueError, match="expected 1024 dimensions"):
+        O.validate_vectors(np.zeros((2, 768), np.float32))
+    bad = np.zeros((2, DIM), np.float32)
+    bad[1, 7] = np.nan
+    with pytest.raises(ValueError, match="NaN or infinite"):
+        O.validate_vectors(bad)
+    bad[1, 7] = np.inf
+    with pytest.raises(ValueError):
+        O.validate_vectors(bad)
+
+
+# ---------------------------------------------------------------- internal consistency
+def test_canon_sum_matches_exact_rational():
+    from fractions import Fraction
+    rng = np.random.default_rng(6)
+    a = rng.standard_normal(1024)
+    exact = float(sum(Fraction(float(v)) for v in a))
+    assert abs(O.canon_sum(a) - exact) <= 1e-12
+    # fixed order: same bits on a second evaluation and for a 2-D batch
+    assert O.canon_sum(a) == O.canon_sum(np.stack([a, a]))[1]
+
+
+def test_shortlist_path_equals_exhaustive(small_table):
+    X, Q, _ = small_table
+    ids = _ids(X.shape[0])
+    for q in Q[:8]:
+        a = O.topk_exact(X, ids, q, K)
+        b = O.topk_exact(X, ids, q, K, exhaustive=True)
+        assert np.array_equal(a[0], b[0])
+        np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_pgv_precision_agrees_with_canonical(small_table):
+    X, Q, _ = small_table
+    ids = _ids(X.shape[0])
+    for q in Q[:8]:
+        c_ids, c_d = O.topk_exact(X, ids, q, K)
+        p_ids, p_d = O.numpy_replica_topk(X, ids, q, K)
+        np.testing.assert_allclose(p_d, c_d, rtol=0, atol=5e-7)    # fp32 accumulators
+        # fp32-ambiguous near-ties may swap neighbours; the SET is stable on this data
+        assert set(O.ids_to_ints(p_ids)) == set(O.ids_to_ints(c_ids))
+
+
+def test_c_restatement_matches_numpy(pgv_lib, small_table):
+    X, Q, _ = small_table
+    n = X.shape[0]
+    ids = _ids(n)
+    rows = np.zeros(K, np.int64)
+    dist = np.zeros(K, np.float64)
+    for q in Q[:4]:
+        q = np.ascontiguousarray(q)
+        m = pgv_lib.pgv_scan_topk(X.ctypes.data, 0, n, DIM, q.ctypes.data, K, rows.ctypes.data, dist.ctypes.data)
+        assert m == K
+        c_ids, c_d = O.topk_exact(X, ids, q, K)
+        np.testing.assert_allclose(dist, c_d, rtol=0, atol=5e-7)
+        assert set(rows.tolist()) == set(O.ids_to_ints(c_ids))
+        rows_mt = np.zeros(K, np.int64)
+        dist_mt = np.zeros(K, np.float64)
+        m = pgv_lib.pgv_scan_topk_mt(X.ctypes.data, n, DIM, q.ctypes.data, K, 4, rows_mt.ctypes.data,
+                                     dist_mt.ctypes.data)
+        assert m == K and np.array_equal(rows_mt, rows) and np.array_equal(dist_mt, dist)
+    d1 = pgv_lib.pgv_cosine_distance(DIM, X[0].ctypes.data, X[0].ctypes.data)
+    assert abs(d1) < 1e-6
+
+
+def test_merge_shards_equals_global(small_table):
+    X, Q, _ = small_table
+    ids = _ids(X.shape[0])
+    q = Q[0]
+    parts = []
+    for s in range(4):
+        sel = np.arange(s, X.shape[0], 4)
+        parts.append(O.topk_exact(X[sel], ids[sel], q, K))
+    g = O.topk_exact(X, ids, q, K)
+    m = O.merge_shards(parts, K)
+    assert np.array_equal(m[0], g[0])
+    np.testing.assert_array_equal(m[1], g[1])
+
+
+# ---------------------------------------------------------------- committed golden vectors
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "topk_golden.json")
+
+
+def test_golden_vectors(synth100k):
+    """tests/golden/topk_golden.json (made by tests/golden/make_golden.py with THIS oracle on
+    the counter-based synthetic table): guards the oracle and the generator against drift."""
+    with open(GOLDEN) as f:
+        G = json.load(f)
+    X = synth100k.table(G["n_rows"])
+    ids = _ids(G["n_rows"])
+    Q, _ = synth100k.queries(len(G["cases"]), G["n_rows"])
+    assert float(X[123, 45]).hex() == G["probe_x_123_45"]
+    for qi, case in enumerate(G["cases"]):
+        got_ids, got_d = O.topk_exact(X, ids, Q[qi], G["k"])
+        assert O.ids_to_ints(got_ids) == case["ids"]
+        assert [float(d).hex() for d in got_d] == case["dist_hex"]
