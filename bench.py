@@ -119,11 +119,15 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(tag: str):
+def traffic_from_profile(tag: str, rows: int):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/traffic.json holds
+    bytes for the captured row count; the scan is linear in rows, so it is scaled to this launch)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get(tag)
+            e = json.load(f).get(tag)
+        if isinstance(e, dict) and e.get("rows"):
+            return e["bytes"] * rows / e["rows"]
     return None
 
 
@@ -321,18 +325,23 @@ def run_ours(a):
     elem = 4 if a.dtype == "fp32" else 2
     bytes_per_launch = owned * DIM * elem
     path = s1["last_path"]
-    if path == 2:       # tcgen05 batched scan: tensor roofline
-        flops = 2.0 * owned * DIM * B
+    flops = 2.0 * owned * DIM * B
+    t_hbm_ideal = bytes_per_launch / (hbm_peak * 1e9)
+    t_tensor_ideal = flops / (tensor_peak * 1e12) * (2.0 if a.dtype == "fp32" else 1.0)   # tf32 runs at half the bf16 rate
+    kernel = "scan_umma" if path == 2 else "scan_gemv"
+    if path == 2 and t_tensor_ideal > t_hbm_ideal:       # large batches: the tensor pipe bounds the scan
         ach = flops / (scan_ms * 1e-3) / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach / tensor_peak,
-                "traffic": traffic_from_profile("scan_umma"), "peak_source": peak_src,
-                "kernel": "scan_umma", "kernel_ms": scan_ms, "hbm_gbs": bytes_per_launch / (scan_ms * 1e-3) / 1e9}
+        peak = tensor_peak * (0.5 if a.dtype == "fp32" else 1.0)
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": traffic_from_profile(f"{kernel}_{a.dtype}_b{B}", owned), "peak_source": peak_src,
+                "kernel": kernel, "kernel_ms": scan_ms, "hbm_gbs": bytes_per_launch / (scan_ms * 1e-3) / 1e9,
+                "algorithmic_flops_per_launch": flops}
     else:
         ach = bytes_per_launch / (scan_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                "traffic": traffic_from_profile("scan_gemv"), "peak_source": peak_src, "kernel": "scan_gemv",
+                "traffic": traffic_from_profile(f"{kernel}_{a.dtype}", owned), "peak_source": peak_src, "kernel": kernel,
                 "kernel_ms": scan_ms, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "frac_of_nominal_8TBs": ach / 8000.0}
+                "frac_of_nominal_8TBs": ach / 8000.0, "tflops": flops / (scan_ms * 1e-3) / 1e12}
     qps = B * a.steps / (total_ms * 1e-3)
     e2e_qps = B * a.steps / (e2e_ms * 1e-3)
     line = {

@@ -65,7 +65,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                 const QueryPrep *__restrict__ prep, const uint64_t *__restrict__ partial_all,
                 int nparts, int k, uint32_t n_rows, double eps, orx_id *__restrict__ out_ids,
                 double *__restrict__ out_dist, int *__restrict__ out_counts,
-                int *__restrict__ out_flags) {
+                int *__restrict__ out_flags, const float *__restrict__ floor_all) {
     constexpr int K = 32 * S;
     __shared__ uint64_t s_keys[FIN_WARPS][K];
     __shared__ uint64_t s_cand[K];
@@ -146,18 +146,33 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     }
     __syncthreads();
 
-    // 4. completeness proof: no row outside the candidate list can sort before the k-th
+    // 4. completeness proof: no row outside the candidate list can sort before the k-th.
+    //    GEMV scan: the lists are each CTA's true top-K, so every outside row has fast score
+    //    <= the merged list's K-th.  tcgen05 scan (floor_all != null): the lists hold every row
+    //    above the CTA's running threshold; outside rows are <= max(final thresholds, merged K-th).
     if (t == 0) {
         out_counts[qi] = count;
         int flag = 1;
-        if (n_rows <= (uint32_t)K) {
+        const bool coarse = floor_all != nullptr;
+        if (!coarse && n_rows <= (uint32_t)K) {
             flag = 0;                                  // every live row is a candidate
         } else if (!prep[qi].zero && !prep[qi].nonfinite) {
             const uint32_t ord_last = key_ord(s_cand[K - 1]);   // K-th best fast score
             const double dk = s_kth;
             if (ord_last == ORD_ALWAYS) flag = 1;      // list flooded by untrusted rows
             else if (dk != dk) flag = 1;               // k-th is NaN: id order among NaN rows unknown
-            else if (ord_last == ORD_NAN) flag = 0;    // everything outside is a NaN row
+            else if (coarse) {
+                // zero-norm rows are never collected by the coarse pass: too few finite rows -> exact scan
+                if (count == k) {
+                    double bound = ord_last == ORD_NAN ? -1.0e30 : (double)ord_to_float(ord_last);
+                    for (int p = 0; p < nparts; ++p) {
+                        const double f = (double)floor_all[(size_t)qi * nparts + p];
+                        if (!(f <= bound)) bound = f;  // also catches NaN / +inf (overflowed list)
+                    }
+                    bound += eps;
+                    flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
+                }
+            } else if (ord_last == ORD_NAN) flag = 0;  // everything outside is a NaN row
             else {
                 const double bound = (double)ord_to_float(ord_last) + eps;
                 flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
@@ -171,27 +186,27 @@ template <typename T>
 static void launch_finalize_t(const void *table, const double *n2, const orx_id *row_ids, const float *q,
                               const QueryPrep *prep, const uint64_t *partial, int nparts, int slots, int nq,
                               int k, uint32_t n_rows, double eps, orx_id *out_ids, double *out_dist,
-                              int *out_counts, int *out_flags, cudaStream_t st) {
+                              int *out_counts, int *out_flags, cudaStream_t st, const float *floor) {
     const T *tab = static_cast<const T *>(table);
     if (slots == 1)
         finalize_kernel<T, 1><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
-                                                          eps, out_ids, out_dist, out_counts, out_flags);
+                                                          eps, out_ids, out_dist, out_counts, out_flags, floor);
     else
         finalize_kernel<T, 2><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
-                                                          eps, out_ids, out_dist, out_counts, out_flags);
+                                                          eps, out_ids, out_dist, out_counts, out_flags, floor);
 }
 
 void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,
                      const float *q, const QueryPrep *prep, const uint64_t *partial, int nparts,
                      int slots, int nq, int k, uint32_t n_rows, double eps, orx_id *out_ids,
-                     double *out_dist, int *out_counts, int *out_flags, cudaStream_t st) {
+                     double *out_dist, int *out_counts, int *out_flags, cudaStream_t st, const float *floor) {
     if (nq <= 0) return;
     if (dtype == ORX_DTYPE_F32)
         launch_finalize_t<float>(table, n2, row_ids, q, prep, partial, nparts, slots, nq, k, n_rows, eps,
-                                 out_ids, out_dist, out_counts, out_flags, st);
+                                 out_ids, out_dist, out_counts, out_flags, st, floor);
     else
         launch_finalize_t<__nv_bfloat16>(table, n2, row_ids, q, prep, partial, nparts, slots, nq, k, n_rows,
-                                         eps, out_ids, out_dist, out_counts, out_flags, st);
+                                         eps, out_ids, out_dist, out_counts, out_flags, st, floor);
 }
 
 // ----------------------------------------------------------------- merge_topk

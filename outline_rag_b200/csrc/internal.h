@@ -9,8 +9,8 @@ namespace orx {
 // Rigorous bounds on |fast score - canonical cosine| per scan path ("Exactness").
 constexpr double EPS_GEMV_F32 = 3.0e-6;   // fp32 FMA chain of depth 32 + 5 shuffle adds
 constexpr double EPS_GEMV_BF16 = 3.0e-6;  // same arithmetic on exactly-converted bf16 rows
-constexpr double EPS_UMMA_TF32 = 2.1e-3;  // tf32 operand truncation (2 * 2^-10) + fp32 accumulate
-constexpr double EPS_UMMA_BF16 = 4.1e-3;  // bf16 query rounding (2^-8 worst case) + fp32 accumulate
+constexpr double EPS_UMMA_TF32 = 2.5e-3;  // both operands cut to 10 mantissa bits: (1+2^-10)^2-1 = 1.96e-3, + accumulation
+constexpr double EPS_UMMA_BF16 = 2.5e-3;  // RNE bf16 query: 2^-9 = 1.96e-3 (rows are exact bf16), + accumulation
 
 // candidate list = 32 * slots keys per query: k <= 16 -> 32 candidates, k <= 32 -> 64
 inline int slots_for_k(int k) { return k <= 16 ? 1 : 2; }
@@ -30,7 +30,7 @@ void launch_finalize(int dtype, const void *table, const double *n2, const orx_i
                      const float *q, const QueryPrep *prep, const uint64_t *partial, int nparts,
                      int slots, int nq, int k, uint32_t n_rows, double eps,
                      orx_id *out_ids, double *out_dist, int *out_counts, int *out_flags,
-                     cudaStream_t st);
+                     cudaStream_t st, const float *floor = nullptr);
 void launch_merge_topk(int n_lists, int nq, int k, const orx_id *ids, const double *dist,
                        const int *counts, orx_id *out_ids, double *out_dist, int *out_counts,
                        cudaStream_t st);

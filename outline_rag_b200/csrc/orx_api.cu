@@ -354,9 +354,10 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         CK(cudaMemsetAsync(ix->res_flags.p, 0, nq * sizeof(int), st));
     } else if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
         path = 2;
+        cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
                                   ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
-                                  out.counts, ix->res_flags.p, st, &ix->stats.kernel_launches);
+                                  out.counts, ix->res_flags.p, st, &ix->stats.kernel_launches, e0, e1);
         if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
     } else {
         int rc = gemv_pass(ix, 0, nq, k, out, ix->res_flags.p);

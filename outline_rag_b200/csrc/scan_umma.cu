@@ -1,13 +1,511 @@
-// placeholder until the tcgen05 scan lands: never selected.
+// scan_umma: the batched scan -- a tcgen05 / TMEM GEMM fed by TMA with the top-k selection
+// fused into the epilogue, so the [queries x rows] score matrix never reaches HBM.
+//
+// Stands in for `ORDER BY embedding <=> :q LIMIT :k` issued for MANY queries at once (the
+// micro-batched form of reference app/rag.py:85-87 -> langchain-postgres SQL).
+//
+// Orientation: queries on M (TMEM lanes), table rows on N (TMEM columns):
+//     D[128 queries x 256 rows] += Qhat[128 x Kc] . X[256 x Kc]^T      (both operands K-major)
+// bf16 tables run kind::f16 (bf16 x bf16 -> fp32), fp32 tables run kind::tf32 on the fp32 bits.
+// Each epilogue thread owns ONE query (one TMEM lane): it reads its accumulator row with
+// tcgen05.ld and tests every column against a private running threshold
+//     thr = (k-th best coarse score seen for this query) - margin,   margin = 2*eps + 1e-6
+// appending survivors (score key | ~row) to a small per-(query, CTA) list in global memory.
+// Every row a thread drops has coarse score <= thr, and k kept rows have coarse >= thr + margin,
+// so with |coarse - cos| <= eps no dropped row can belong to the top-k: the candidate set is
+// COMPLETE by construction; finalize_kernel rescoring makes it exact and re-proves it
+// (floor = the largest final thr of the query's CTAs).  Thresholds are shared between CTAs
+// through an atomicMax'd per-query word, so the bootstrap flood is paid about once.
+//
+// Warp roles (256 threads, 1 CTA / SM, persistent): warp 0 = TMA producer, warp 1 = MMA issuer
+// (one lane), warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM lane quarter = warp % 4).
+// Pipelines: smem full/empty ring (4 stages x 48 KB) and a 2 x 256-column TMEM accumulator
+// ring, so the epilogue of tile i overlaps the MMAs of tile i+1.
+// CTA c works on query tile m = c % m_tiles and row tiles slot, slot + n_slots, ... with
+// slot = c / m_tiles: the m_tiles CTAs of a slot stream the same table tile at the same time,
+// so it is read from HBM once and served from L2 to the others.
+// Algorithmic work per launch: bytes = rows*1024*sizeof(elem); flops = 2*rows*1024*queries.
+#include <cuda.h>
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
 #include "scan_umma.h"
+
 namespace orx {
-struct UmmaPlan { int device; };
-UmmaPlan *umma_plan_create(int device) { return new UmmaPlan{device}; }
-void umma_plan_destroy(UmmaPlan *p) { delete p; }
-void umma_plan_invalidate(UmmaPlan *) {}
-bool umma_should_use(const UmmaPlan *, int, uint32_t) { return false; }
-const char *umma_last_error() { return "tcgen05 scan not built"; }
-int umma_search(UmmaPlan *, int, const void *, const float *, const double *, const orx_id *, uint32_t,
-                const float *, const float *, const __nv_bfloat16 *, const QueryPrep *, int, int, orx_id *,
-                double *, int *, int *, cudaStream_t, uint64_t *) { return ORX_ERR_INVALID; }
+
+namespace {
+
+constexpr int UM_THREADS = 256;
+constexpr int TILE_M = 128;            // queries per CTA tile (UMMA M)
+constexpr int TILE_N = 256;            // table rows per tile (UMMA N)
+constexpr int STAGES = 4;
+constexpr int A_BYTES = TILE_M * 128;  // 16 KB: 128 rows x one 128-byte swizzle row of K
+constexpr int B_BYTES = TILE_N * 128;  // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int CAND = 64;               // candidate slots per (query, CTA) = finalize S=2 list
+constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;
+constexpr int SMEM_SCALE = 2 * TILE_N * 4;
+constexpr int SMEM_TOTAL = SMEM_MAIN + SMEM_SCALE + 256 + 1024;   // + barriers + alignment slack
+
+constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
+
+// ------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// Bounded wait: a pipeline bug traps (launch failure) after ~4 s instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    uint64_t t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+        if ((it & 1023u) == 1023u) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                            uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 "version 1"):
+// start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(= 8 rows x 128 B = 1024 B)>>4 <<32 | layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+    return d;
+}
+// instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32) {
+    return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
+           ((uint32_t)(TILE_M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ candidate list upkeep
+// Called when a thread's list is full (or at the end of the CTA's work): raise the threshold to
+// (k-th best REGULAR coarse score) - margin, drop what fell below it, publish the threshold.
+__device__ __noinline__ void compact_candidates(uint64_t *buf, int &cnt, float &thr, int k, float margin,
+                                                bool &overflow, uint32_t *gthr) {
+    const int n = cnt;
+    int n_reg = 0;
+    for (int i = 0; i < n; ++i) n_reg += (key_ord(buf[i]) != ORD_ALWAYS);
+    if (n_reg >= k) {
+        uint32_t kth = 0;
+        for (int i = 0; i < n; ++i) {
+            const uint64_t ki = buf[i];
+            if (key_ord(ki) == ORD_ALWAYS) continue;
+            int rank = 0;
+            for (int j = 0; j < n; ++j) {
+                const uint64_t kj = buf[j];
+                rank += (key_ord(kj) != ORD_ALWAYS && kj > ki);
+            }
+            if (rank == k - 1) kth = key_ord(ki);
+        }
+        float t = ord_to_float(kth) - margin;
+        int w = 0;
+        if (t > thr) thr = t;
+        for (int i = 0; i < n; ++i) {
+            const uint64_t ki = buf[i];
+            if (key_ord(ki) == ORD_ALWAYS || ord_to_float(key_ord(ki)) > thr) buf[w++] = ki;
+        }
+        cnt = w;
+        if (cnt > CAND - 8) {
+            // near-ties wider than the list: the query is re-answered by the fp32 scan; stop collecting
+            overflow = true;
+            thr = __int_as_float(0x7f800000);
+            cnt = CAND - 8;
+        }
+        atomicMax(gthr, float_to_ord(thr));
+    } else if (n >= CAND) {               // list full of untrusted (irregular) rows
+        overflow = true;
+        thr = __int_as_float(0x7f800000);
+        cnt = CAND - 8;
+    }
+}
+
+__device__ __forceinline__ void append_candidate(uint64_t *buf, int &cnt, float &thr, uint64_t key, int k,
+                                                 float margin, bool &overflow, uint32_t *gthr) {
+    buf[cnt] = key;
+    if (++cnt == CAND) compact_candidates(buf, cnt, thr, k, margin, overflow, gthr);
+}
+
+template <bool TF32>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                 const float *__restrict__ scale, uint32_t n_rows, int nq, int m_tiles, int n_slots, int k,
+                 float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
+                 uint32_t *__restrict__ gthr_all) {
+    constexpr int ES = TF32 ? 4 : 2;                // operand element size
+    constexpr int BLOCK_K = 128 / ES;               // elements per 128-byte swizzle row
+    constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;     // 16 (bf16) / 32 (tf32)
+    constexpr uint32_t IDESC = make_idesc(TF32);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *s_scale = reinterpret_cast<float *>(smem + SMEM_MAIN);               // [2][TILE_N]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SMEM_MAIN + SMEM_SCALE);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 16);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(bars);            // [STAGES]
+    const uint32_t bar_empty = bar_full + 8 * STAGES;    // [STAGES]
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES;   // [2]
+    const uint32_t bar_tempty = bar_tfull + 16;          // [2]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x % m_tiles;
+    const int slot = blockIdx.x / m_tiles;
+    const uint32_t n_tiles = (n_rows + TILE_N - 1) / TILE_N;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 4);            // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+            const uint64_t hint_x = (m_tiles > 1) ? HINT_EVICT_NORMAL : HINT_EVICT_FIRST;
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = slot; t < n_tiles; t += n_slots) {
+                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+                    tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * BLOCK_K, m_tile * TILE_M, HINT_EVICT_LAST);
+                    tma_load_2d(sa + A_BYTES, &map_x, bar_full + 8 * stage, kc * BLOCK_K, (int)(t * TILE_N), hint_x);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================================= MMA issuer
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
+            for (uint32_t t = slot; t < n_tiles; t += n_slots) {
+                mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);       // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * TILE_N;
+                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE_BYTES;
+                    const uint64_t adesc = make_desc_sw128(sa);
+                    const uint64_t bdesc = make_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)             // 4 x (32 bytes of K) per swizzle row
+                        tc_mma<TF32>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, IDESC, (kc | k4) != 0 ? 1u : 0u);
+                    tc_commit(bar_empty + 8 * stage);           // frees the smem stage when the MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                tc_commit(bar_tfull + 8 * buf);                 // accumulator ready for the epilogue
+                if (++buf == 2) { buf = 0; tphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ========================================================================= epilogue
+        const int ew = warp - 4;                                // == warp % 4: TMEM lane quarter
+        const int et = threadIdx.x - 128;                       // 0..127
+        const int q = m_tile * TILE_M + ew * 32 + lane;
+        const bool active = q < nq;
+        uint64_t *buf_keys = partial + ((size_t)(active ? q : 0) * n_slots + slot) * CAND;
+        uint32_t *gthr = gthr_all + (active ? q : 0);
+        float thr = __int_as_float(0xff800000);                 // -inf
+        int cnt = 0;
+        bool overflow = false;
+        uint32_t buf = 0, tphase = 0;
+        for (uint32_t t = slot; t < n_tiles; t += n_slots) {
+            const uint32_t n0 = t * TILE_N;
+            // stage this tile's 1/|x| (NaN beyond the table end: never a candidate)
+            float *sc = s_scale + buf * TILE_N;
+            bool special = false;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t r = n0 + et + 128 * h;
+                const float s = r < n_rows ? __ldg(scale + r) : __int_as_float(0x7fc00000);
+                special |= !(fabsf(s) < __int_as_float(0x7f800000));      // inf or NaN
+                sc[et + 128 * h] = s;
+            }
+            uint32_t tile_special;
+            asm volatile(
+                "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\t"
+                "bar.red.or.pred p, 1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(tile_special) : "r"((uint32_t)special) : "memory");
+            if (active) {
+                const uint32_t g = *reinterpret_cast<volatile uint32_t *>(gthr);
+                if (g) thr = fmaxf(thr, ord_to_float(g));
+            }
+            mbar_wait(bar_tfull + 8 * buf, tphase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * TILE_N;
+#pragma unroll 1
+            for (int c = 0; c < TILE_N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(taddr + c * 32, v);
+                tmem_ld_wait();
+                if (!active) continue;
+                const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c * 32);
+                if (!tile_special) {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 s4 = sc4[j4];
+                        const float s0 = __uint_as_float(v[4 * j4 + 0]) * s4.x;
+                        const float s1 = __uint_as_float(v[4 * j4 + 1]) * s4.y;
+                        const float s2 = __uint_as_float(v[4 * j4 + 2]) * s4.z;
+                        const float s3 = __uint_as_float(v[4 * j4 + 3]) * s4.w;
+                        const uint32_t row = n0 + c * 32 + 4 * j4;
+                        if (s0 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s0), row + 0), k, margin, overflow, gthr);
+                        if (s1 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s1), row + 1), k, margin, overflow, gthr);
+                        if (s2 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s2), row + 2), k, margin, overflow, gthr);
+                        if (s3 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s3), row + 3), k, margin, overflow, gthr);
+                    }
+                } else {
+                    // tile holds zero-norm / irregular / out-of-range rows: classify every column
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sj = sc[c * 32 + j];
+                        if (sj != sj) continue;                                   // zero-norm or beyond the end
+                        const uint32_t row = n0 + c * 32 + j;
+                        if (sj == __int_as_float(0x7f800000)) {                   // irregular magnitude: always kept
+                            if (!overflow) append_candidate(buf_keys, cnt, thr, make_key(ORD_ALWAYS, row), k, margin, overflow, gthr);
+                            continue;
+                        }
+                        const float s = __uint_as_float(v[j]) * sj;
+                        if (s > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s), row), k, margin, overflow, gthr);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
+            if (++buf == 2) { buf = 0; tphase ^= 1; }
+        }
+        if (active) {
+            for (int i = cnt; i < CAND; ++i) buf_keys[i] = 0ull;
+            floor_out[(size_t)q * n_slots + slot] = overflow ? __int_as_float(0x7f800000) : thr;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+thread_local std::string g_umma_err;
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        cudaGetLastError();
+    });
+    return fn;
+}
+
+// [rows, 1024] K-major matrix, box = one 128-byte swizzle row of K x box_rows rows
+bool encode_map(CUtensorMap *map, const void *base, uint64_t rows, bool fp32, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) { g_umma_err = "cuTensorMapEncodeTiled entry point not found"; return false; }
+    const cuuint64_t dims[2] = {ORX_DIM, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ORX_DIM * (fp32 ? 4 : 2)};
+    const cuuint32_t box[2] = {(cuuint32_t)(fp32 ? 32 : 64), box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                    const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        g_umma_err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+struct UmmaPlan {
+    int device = 0;
+    int sms = 148;
+    bool attr_set = false;
+    uint64_t *partial = nullptr;
+    size_t partial_n = 0;
+    float *floor = nullptr;
+    size_t floor_n = 0;
+    uint32_t *gthr = nullptr;
+    size_t gthr_n = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+UmmaPlan *umma_plan_create(int device) {
+    UmmaPlan *p = new UmmaPlan();
+    p->device = device;
+    cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
+    return p;
+}
+void umma_plan_destroy(UmmaPlan *p) {
+    if (!p) return;
+    cudaFree(p->partial);
+    cudaFree(p->floor);
+    cudaFree(p->gthr);
+    delete p;
+}
+void umma_plan_invalidate(UmmaPlan *) {}      // tensor maps are encoded per search (pointer + live row count)
+const char *umma_last_error() { return g_umma_err.c_str(); }
+
+bool umma_should_use(const UmmaPlan *p, int nq, uint32_t n_rows) {
+    // one table pass for the whole batch beats nq GEMV passes as soon as nq >= 2
+    return p != nullptr && nq >= 2 && n_rows >= 4096;
+}
+
+template <typename T>
+static cudaError_t ensure_buf(T *&ptr, size_t &have, size_t want) {
+    if (want <= have) return cudaSuccess;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    have = 0;
+    cudaError_t e = cudaMalloc(&ptr, want * sizeof(T));
+    if (e == cudaSuccess) have = want;
+    return e;
+}
+
+int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, const double *n2,
+                const orx_id *row_ids, uint32_t n_rows, const float *q_dev, const float *qhat,
+                const __nv_bfloat16 *qhat16, const QueryPrep *prep, int nq, int k, orx_id *out_ids,
+                double *out_dist, int *out_counts, int *out_flags, cudaStream_t st, uint64_t *launch_counter,
+                cudaEvent_t ev_begin, cudaEvent_t ev_end) {
+    const bool tf32 = dtype == ORX_DTYPE_F32;
+    const double eps = tf32 ? EPS_UMMA_TF32 : EPS_UMMA_BF16;
+    const float margin = (float)(2.0 * eps + 1e-6);
+    if (!p->attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(scan_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(scan_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
+        p->attr_set = true;
+    }
+    constexpr int MAX_Q = 2048;              // 16 query tiles -> 9 row slots -> 144 CTAs
+    for (int q0 = 0; q0 < nq; q0 += MAX_Q) {
+        const int m = nq - q0 < MAX_Q ? nq - q0 : MAX_Q;
+        const int m_tiles = (m + TILE_M - 1) / TILE_M;
+        const uint32_t n_tiles = (n_rows + TILE_N - 1) / TILE_N;
+        int n_slots = p->sms / m_tiles;
+        if (n_slots < 1) n_slots = 1;
+        if ((uint32_t)n_slots > n_tiles) n_slots = (int)n_tiles;
+        cudaError_t e = ensure_buf(p->partial, p->partial_n, (size_t)m * n_slots * CAND);
+        if (e == cudaSuccess) e = ensure_buf(p->floor, p->floor_n, (size_t)m * n_slots);
+        if (e == cudaSuccess) e = ensure_buf(p->gthr, p->gthr_n, (size_t)m);
+        if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
+        CUtensorMap map_q, map_x;
+        const void *qbase = tf32 ? (const void *)(qhat + (size_t)q0 * ORX_DIM) : (const void *)(qhat16 + (size_t)q0 * ORX_DIM);
+        if (!encode_map(&map_q, qbase, (uint64_t)m, tf32, TILE_M)) return ORX_ERR_CUDA;
+        if (!encode_map(&map_x, table, (uint64_t)n_rows, tf32, TILE_N)) return ORX_ERR_CUDA;
+        cudaMemsetAsync(p->gthr, 0, (size_t)m * sizeof(uint32_t), st);
+        if (ev_begin && q0 == 0) cudaEventRecord(ev_begin, st);
+        const int grid = m_tiles * n_slots;
+        if (tf32)
+            scan_umma_kernel<true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
+                                                                         k, margin, p->partial, p->floor, p->gthr);
+        else
+            scan_umma_kernel<false><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
+                                                                          k, margin, p->partial, p->floor, p->gthr);
+        if (ev_end && q0 + MAX_Q >= nq) cudaEventRecord(ev_end, st);
+        launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, 2, m,
+                        k, n_rows, eps, out_ids + (size_t)q0 * k, out_dist + (size_t)q0 * k, out_counts + q0,
+                        out_flags + q0, st, p->floor);
+        *launch_counter += 2;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
+    }
+    return ORX_OK;
+}
+
+}  // namespace orx

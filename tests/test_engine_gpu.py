@@ -363,3 +363,53 @@ def test_merge_handles_short_lists(Index, small_table):
         w_ids, w_d = O.topk_exact(X[:8], allids, Q[i], K)
         assert m[2][i] == 8 and np.array_equal(m[0][i, :8], w_ids)
         assert np.array_equal(m[1][i, :8].view(np.uint64), w_d.view(np.uint64))
+
+
+# ------------------------------------------------------------------ tcgen05 batched scan
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+@pytest.mark.parametrize("nq", [2, 32, 128, 129, 300])
+def test_tcgen05_batched_scan_is_exact(Index, synth100k, dtype, nq):
+    """Query batches run the TMA + tcgen05 coarse scan with the fused threshold-collect epilogue;
+    results must still equal the oracle bit for bit (canonical rescore + completeness proof)."""
+    n = 20000
+    X = synth100k.table(n)
+    Q, _ = synth100k.queries(nq, n)
+    ids = _ids(n)
+    rows = X if dtype == "fp32" else stored_bf16_rows(X)
+    with Index(dtype) as ix:
+        ix.upsert(ids, X)
+        _check_exact(ix, X, ids, Q, oracle_rows=rows)
+        st = ix.stats()
+    assert st["last_path"] == 2
+    assert st["fallback_gemv"] <= max(1, nq // 16), st        # the coarse pass proves almost every query itself
+
+
+def test_tcgen05_ragged_rows_special_rows_and_k32(Index, synth100k):
+    n = 4096 + 77                                             # last tile is partial
+    X = synth100k.table(n).copy()
+    X[100] = 0.0                                              # zero-norm row: NaN distance, never a candidate
+    X[200] *= np.float32(1e30)                                # irregular magnitude: always a candidate
+    X[4100] *= np.float32(1e-30)
+    Q, _ = synth100k.queries(40, n)
+    Q = np.concatenate([Q, X[200:201] / np.float32(1e30), X[4100:4101] * np.float32(1e30)])
+    ids = _ids(n)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        _check_exact(ix, X, ids, Q, k=32)
+        _check_exact(ix, X, ids, Q, k=1)
+        assert ix.stats()["last_path"] == 2
+
+
+def test_tcgen05_duplicates_overflow_falls_back(Index, synth100k):
+    n = 6000
+    X = synth100k.table(n).copy()
+    X[1000:1200] = X[5]                                       # 200 identical rows: wider than any candidate list
+    rng = np.random.default_rng(3)
+    idv = rng.permutation(n) + 10
+    ids = O.ids_from_ints(idv.tolist())
+    Q = np.stack([X[5], X[7], X[9]])
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        _check_exact(ix, X, ids, Q)
+        st = ix.stats()
+    assert st["fallback_gemv"] >= 1 and st["fallback_exhaustive"] >= 1
