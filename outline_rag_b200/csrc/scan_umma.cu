@@ -140,51 +140,43 @@ __host__ __device__ constexpr uint32_t make_idesc(bool tf32) {
 }
 
 // ------------------------------------------------------------------ candidate list upkeep
-// Called when a thread's list is full (or at the end of the CTA's work): raise the threshold to
-// (k-th best REGULAR coarse score) - margin, drop what fell below it, publish the threshold.
-__device__ __noinline__ void compact_candidates(uint64_t *buf, int &cnt, float &thr, int k, float margin,
-                                                bool &overflow, uint32_t *gthr) {
-    const int n = cnt;
-    int n_reg = 0;
-    for (int i = 0; i < n; ++i) n_reg += (key_ord(buf[i]) != ORD_ALWAYS);
-    if (n_reg >= k) {
-        uint32_t kth = 0;
-        for (int i = 0; i < n; ++i) {
-            const uint64_t ki = buf[i];
-            if (key_ord(ki) == ORD_ALWAYS) continue;
-            int rank = 0;
-            for (int j = 0; j < n; ++j) {
-                const uint64_t kj = buf[j];
-                rank += (key_ord(kj) != ORD_ALWAYS && kj > ki);
-            }
-            if (rank == k - 1) kth = key_ord(ki);
-        }
-        float t = ord_to_float(kth) - margin;
-        int w = 0;
-        if (t > thr) thr = t;
-        for (int i = 0; i < n; ++i) {
-            const uint64_t ki = buf[i];
-            if (key_ord(ki) == ORD_ALWAYS || ord_to_float(key_ord(ki)) > thr) buf[w++] = ki;
-        }
-        cnt = w;
-        if (cnt > CAND - 8) {
-            // near-ties wider than the list: the query is re-answered by the fp32 scan; stop collecting
-            overflow = true;
-            thr = __int_as_float(0x7f800000);
-            cnt = CAND - 8;
-        }
-        atomicMax(gthr, float_to_ord(thr));
-    } else if (n >= CAND) {               // list full of untrusted (irregular) rows
-        overflow = true;
-        thr = __int_as_float(0x7f800000);
-        cnt = CAND - 8;
+// Warp-cooperative compaction of lane L's candidate list (<= 64 keys, two per lane): raise L's
+// threshold to (k-th best REGULAR coarse score) - margin, keep what is still above it (and every
+// ORD_ALWAYS key), publish the threshold.  All 32 lanes call this with the same L.
+__device__ __forceinline__ void coop_compact(uint64_t *list, int L, int lane, int &cnt, float &thr, int k,
+                                             float margin, uint32_t *gthr_L) {
+    __syncwarp();                                    // lane L's appends are visible to the warp
+    const int n = __shfl_sync(FULL_MASK, cnt, L);
+    const float thr_L = __shfl_sync(FULL_MASK, thr, L);
+    const uint64_t k0 = lane < n ? list[lane] : 0ull;
+    const uint64_t k1 = lane + 32 < n ? list[lane + 32] : 0ull;
+    const bool a0 = key_ord(k0) == ORD_ALWAYS, a1 = key_ord(k1) == ORD_ALWAYS;
+    const uint64_t r0 = a0 ? 0ull : k0, r1 = a1 ? 0ull : k1;       // regular keys only take part in the ranking
+    int rank0 = 0, rank1 = 0;
+#pragma unroll 8
+    for (int s = 0; s < 32; ++s) {
+        const uint64_t x = shfl_u64(r0, s), y = shfl_u64(r1, s);
+        rank0 += (x > r0) + (y > r0);
+        rank1 += (x > r1) + (y > r1);
     }
-}
-
-__device__ __forceinline__ void append_candidate(uint64_t *buf, int &cnt, float &thr, uint64_t key, int k,
-                                                 float margin, bool &overflow, uint32_t *gthr) {
-    buf[cnt] = key;
-    if (++cnt == CAND) compact_candidates(buf, cnt, thr, k, margin, overflow, gthr);
+    // keys are unique (distinct rows), so exactly one regular key has rank k-1 when >= k exist
+    const uint32_t mine = (r0 != 0ull && rank0 == k - 1) ? key_ord(r0) : ((r1 != 0ull && rank1 == k - 1) ? key_ord(r1) : 0u);
+    const uint32_t kth = __reduce_max_sync(FULL_MASK, mine);
+    float new_thr = thr_L;
+    if (kth != 0u) new_thr = fmaxf(thr_L, ord_to_float(kth) - margin);
+    const bool keep0 = k0 != 0ull && (a0 || ord_to_float(key_ord(k0)) > new_thr);
+    const bool keep1 = k1 != 0ull && (a1 || ord_to_float(key_ord(k1)) > new_thr);
+    const unsigned b0 = __ballot_sync(FULL_MASK, keep0), b1 = __ballot_sync(FULL_MASK, keep1);
+    const unsigned lt = (1u << lane) - 1u;
+    __syncwarp();
+    if (keep0) list[__popc(b0 & lt)] = k0;
+    if (keep1) list[__popc(b0) + __popc(b1 & lt)] = k1;
+    __syncwarp();
+    if (lane == L) {
+        cnt = __popc(b0) + __popc(b1);
+        thr = new_thr;
+        if (kth != 0u) atomicMax(gthr_L, float_to_ord(new_thr));
+    }
 }
 
 template <bool TF32>
@@ -319,36 +311,64 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 uint32_t v[32];
                 tmem_ld32(taddr + c * 32, v);
                 tmem_ld_wait();
-                if (!active) continue;
                 const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c * 32);
-                if (!tile_special) {
+                float s[32];
+                float mx = __int_as_float(0xff800000);
 #pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const float4 s4 = sc4[j4];
-                        const float s0 = __uint_as_float(v[4 * j4 + 0]) * s4.x;
-                        const float s1 = __uint_as_float(v[4 * j4 + 1]) * s4.y;
-                        const float s2 = __uint_as_float(v[4 * j4 + 2]) * s4.z;
-                        const float s3 = __uint_as_float(v[4 * j4 + 3]) * s4.w;
-                        const uint32_t row = n0 + c * 32 + 4 * j4;
-                        if (s0 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s0), row + 0), k, margin, overflow, gthr);
-                        if (s1 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s1), row + 1), k, margin, overflow, gthr);
-                        if (s2 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s2), row + 2), k, margin, overflow, gthr);
-                        if (s3 > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s3), row + 3), k, margin, overflow, gthr);
-                    }
-                } else {
-                    // tile holds zero-norm / irregular / out-of-range rows: classify every column
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 f = sc4[j4];
+                    s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * f.x;
+                    s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
+                    s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
+                    s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
+                    mx = fmaxf(fmaxf(mx, fmaxf(s[4 * j4 + 0], s[4 * j4 + 1])), fmaxf(s[4 * j4 + 2], s[4 * j4 + 3]));
+                }
+                // fmaxf ignores NaN (zero-norm rows, rows beyond the end); irregular rows need the slow path
+                const bool hit = active && ((mx > thr) || tile_special);
+                if (!__any_sync(FULL_MASK, hit)) continue;
+                // ---- slow path (warp-uniform): some lane has survivors in these 32 columns
+                uint32_t always = 0;
+                if (tile_special) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         const float sj = sc[c * 32 + j];
-                        if (sj != sj) continue;                                   // zero-norm or beyond the end
-                        const uint32_t row = n0 + c * 32 + j;
-                        if (sj == __int_as_float(0x7f800000)) {                   // irregular magnitude: always kept
-                            if (!overflow) append_candidate(buf_keys, cnt, thr, make_key(ORD_ALWAYS, row), k, margin, overflow, gthr);
-                            continue;
-                        }
-                        const float s = __uint_as_float(v[j]) * sj;
-                        if (s > thr) append_candidate(buf_keys, cnt, thr, make_key(float_to_ord(s), row), k, margin, overflow, gthr);
+                        if (sj == __int_as_float(0x7f800000)) always |= 1u << j;      // irregular magnitude
+                        else if (sj != sj) s[j] = __int_as_float(0xff800000);         // zero-norm / beyond the end
                     }
+                }
+                uint32_t mask = 0;
+                for (int round = 0;; ++round) {
+                    mask = 0;
+                    if (active) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= (s[j] > thr) ? (1u << j) : 0u;
+                        mask = (mask & ~always) | (overflow ? 0u : always);
+                    }
+                    const unsigned need = __ballot_sync(FULL_MASK, active && cnt + __popc(mask) > CAND);
+                    if (!need) break;
+                    if (round == 1) {
+                        // near-ties wider than the list: the query is re-answered by the fp32 scan
+                        if (need & (1u << lane)) {
+                            overflow = true;
+                            thr = __int_as_float(0x7f800000);
+                            atomicMax(gthr, float_to_ord(thr));
+                        }
+                        continue;
+                    }
+                    unsigned todo = need;
+                    while (todo) {
+                        const int L = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        uint64_t *list_L = partial + ((size_t)(q - lane + L) * n_slots + slot) * CAND;
+                        coop_compact(list_L, L, lane, cnt, thr, k, margin, gthr_all + (q - lane + L));
+                    }
+                }
+                if (mask) {
+                    const uint32_t row0 = n0 + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (mask & (1u << j))
+                            buf_keys[cnt++] = make_key((always >> j) & 1u ? ORD_ALWAYS : float_to_ord(s[j]), row0 + j);
                 }
             }
             tc_fence_before();
