@@ -233,7 +233,9 @@ def run_ours(a):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        import datetime
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"),
+                                timeout=datetime.timedelta(seconds=180))
     B = a.batch
     per_rank_cap = a.rows // world + a.rows // (world * 8) + 4096
     sh = ShardedIndex(a.dtype, per_rank_cap if world > 1 else a.rows, local)
@@ -296,9 +298,10 @@ def run_ours(a):
 
     # correctness spot check against the oracle on host-regenerated rows (never inside the timed region)
     verify = {}
+    if a.verify > 0:
+        ids_d, dist_d, cnt_d = step_device(0)          # collective: every rank takes part
     if rank == 0 and a.verify > 0:
         from oracle import cosine_topk as O
-        ids_d, dist_d, cnt_d = step_device(0)
         ids_h = ids_d.cpu().numpy().view(np.uint64)
         dist_h = dist_d.cpu().numpy()
         ok = True

@@ -54,7 +54,7 @@ typedef struct orx_stats {
     uint64_t fallback_exhaustive; /* queries answered by the threshold-collect pass */
     uint64_t rows_moved;          /* rows relocated by delete compaction           */
     float    last_scan_ms;        /* device time of the last search's scan kernel(s) */
-    float    last_search_ms;      /* device time of the last search, first to last kernel */
+    float    last_search_ms;      /* host wall time of the last orx_search call     */
     int      last_path;           /* 0 none, 1 gemv scan, 2 tcgen05 scan           */
     int      reserved;
     uint64_t scan_launches;       /* scan kernel launches (gemv or tcgen05)        */
@@ -108,6 +108,15 @@ int orx_search(orx_index *idx, const float *queries, int nq, int dim, int k,
 int orx_merge_topk(orx_index *idx, int n_lists, int nq, int k,
                    const orx_id *ids, const double *dist, const int *counts,
                    orx_id *out_ids, double *out_dist, int *out_counts);
+
+/* Same merge, reading the lists where an allgather left them: every rank contributes ONE block
+ * holding its ids, distances and counts, rank l's block starts l*list_stride_bytes after rank 0's.
+ * ids0 / dist0 / counts0 point at rank 0's arrays inside the gathered buffer.  Device pointers
+ * only; asynchronous on the index's stream (outline_rag_b200/sharded.py). */
+int orx_merge_topk_strided(orx_index *idx, int n_lists, int nq, int k,
+                           const orx_id *ids0, const double *dist0, const int *counts0,
+                           uint64_t list_stride_bytes,
+                           orx_id *out_ids, double *out_dist, int *out_counts);
 
 /* Read back stored rows (as fp32) by id -- snapshot / debugging / tests.
  * out_vecs [n, dim] host; out_found [n] host (1/0). */

@@ -15,8 +15,9 @@ namespace orx {
 // One warp per query: pgvector's input check (NaN/Inf -> error), canonical |q|^2,
 // normalised fp32 copy qhat (and its RNE bf16 image for the tcgen05 bf16 scan).
 __global__ void __launch_bounds__(128)
-prep_queries_kernel(const float *__restrict__ q_all, int nq, float *__restrict__ qhat_all,
-                    __nv_bfloat16 *__restrict__ qhat16_all, QueryPrep *__restrict__ prep) {
+prep_queries_kernel(const float *__restrict__ q_all, int nq, float *__restrict__ q_copy,
+                    float *__restrict__ qhat_all, __nv_bfloat16 *__restrict__ qhat16_all,
+                    QueryPrep *__restrict__ prep) {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (qi >= nq) return;
@@ -26,7 +27,8 @@ prep_queries_kernel(const float *__restrict__ q_all, int nq, float *__restrict__
     bool bad = false;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
-        x[j] = q[lane + 32 * j];
+        x[j] = q[lane + 32 * j];            // may be mapped host memory (zero-copy upload of small batches)
+        if (q_copy) q_copy[(size_t)qi * ORX_DIM + lane + 32 * j] = x[j];
         bad |= !isfinite(x[j]);
         p[j] = __dmul_rn((double)x[j], (double)x[j]);
     }
@@ -47,16 +49,23 @@ prep_queries_kernel(const float *__restrict__ q_all, int nq, float *__restrict__
     }
 }
 
-void launch_prep_queries(const float *q, int nq, float *qhat, void *qhat_bf16, QueryPrep *prep,
-                         cudaStream_t st) {
+void launch_prep_queries(const float *q, int nq, float *q_copy, float *qhat, void *qhat_bf16,
+                         QueryPrep *prep, cudaStream_t st) {
     if (nq <= 0) return;
-    prep_queries_kernel<<<(nq + 3) / 4, 128, 0, st>>>(q, nq, qhat,
+    prep_queries_kernel<<<(nq + 3) / 4, 128, 0, st>>>(q, nq, q_copy, qhat,
                                                       static_cast<__nv_bfloat16 *>(qhat_bf16), prep);
 }
 
 // ------------------------------------------------------------------- finalize
-constexpr int FIN_THREADS = 256;
+// One CTA of 16 warps per query (512 threads: the binary64 rescore needs ~100 registers).
+//   1. every warp folds its share of the per-CTA candidate lists into a register-resident sorted
+//      top-K (K = 32*S), then a 4-level tree merge through shared memory leaves the query's top-K;
+//   2. canonical binary64 rescore, one warp per candidate (all K in flight at once);
+//   3. rank by (distance ASC, NaN last, id ASC) by counting;
+//   4. completeness proof -> flag (bit 0: unproven, bit 1: non-finite query, bit 2: zero query).
+constexpr int FIN_THREADS = 512;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
+constexpr int FIN_SURV = 256;          // survivors of the head-threshold filter (fast path)
 
 template <typename T, int S>
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -65,38 +74,93 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                 const QueryPrep *__restrict__ prep, const uint64_t *__restrict__ partial_all,
                 int nparts, int k, uint32_t n_rows, double eps, orx_id *__restrict__ out_ids,
                 double *__restrict__ out_dist, int *__restrict__ out_counts,
-                int *__restrict__ out_flags, const float *__restrict__ floor_all) {
+                int *__restrict__ out_flags, const float *__restrict__ floor_all, int sorted_lists) {
     constexpr int K = 32 * S;
     __shared__ uint64_t s_keys[FIN_WARPS][K];
-    __shared__ uint64_t s_cand[K];
     __shared__ double s_dist[K];
     __shared__ uint64_t s_hi[K], s_lo[K];
     __shared__ double s_kth;
+    __shared__ int s_valid;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int qi = blockIdx.x;
     const uint64_t *partial = partial_all + (size_t)qi * nparts * K;
-    const int total = nparts * K;
-    if (threadIdx.x == 0) s_kth = __longlong_as_double(0x7ff8000000000000ll);
+    if (threadIdx.x == 0) {
+        s_kth = __longlong_as_double(0x7ff8000000000000ll);
+        s_valid = 0;
+    }
 
-    // 1. fold the per-CTA lists into the query's top-K fast candidates
-    WarpTopK<S> top;
-    top.init();
-    for (int base = warp * 32; base < total; base += FIN_WARPS * 32) {
-        const int i = base + lane;
-        top.offer_lanes(i < total ? partial[i] : 0ull, lane);
-    }
-    top.store(s_keys[warp], lane);
-    __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < FIN_WARPS; ++w) {
-#pragma unroll
-            for (int s = 0; s < S; ++s) top.offer_lanes(s_keys[w][s * 32 + lane], lane);
+    // 1. the query's top-K candidates by fast score.
+    __shared__ uint64_t s_surv[FIN_SURV];
+    __shared__ uint64_t s_thresh;
+    __shared__ int s_nsurv;
+    uint64_t *s_flat = &s_keys[0][0];                   // FIN_WARPS*K >= 512 words of scratch
+    bool fast = sorted_lists && nparts >= K && nparts <= FIN_THREADS;
+    if (fast) {
+        // 1a (sorted lists, GEMV scan): the K-th largest list HEAD is a lower bound of the global
+        //     K-th best key, so only keys >= it can matter -- typically a few dozen of nparts*K.
+        if (threadIdx.x == 0) {
+            s_nsurv = 0;
+            s_thresh = 0ull;
         }
-        top.store(s_cand, lane);
+        const uint64_t head = threadIdx.x < nparts ? partial[(size_t)threadIdx.x * K] : 0ull;
+        s_flat[threadIdx.x] = head;
+        __syncthreads();
+        if (threadIdx.x < nparts) {
+            int rank = 0;
+            for (int i = 0; i < nparts; ++i) rank += (s_flat[i] > head);
+            if (rank == K - 1) s_thresh = head;         // heads are distinct rows (or 0: then rank >= #nonzero)
+        }
+        __syncthreads();
+        const uint64_t T = s_thresh;
+        const int total = nparts * K;
+        for (int i = threadIdx.x; i < total; i += FIN_THREADS) {
+            const uint64_t key = partial[i];
+            if (key >= T && key != 0ull) {
+                const int pos = atomicAdd(&s_nsurv, 1);
+                if (pos < FIN_SURV) s_surv[pos] = key;
+            }
+        }
+        __syncthreads();
+        const int ns = s_nsurv;
+        if (T == 0ull || ns > FIN_SURV) fast = false;   // fewer than K non-empty lists, or a flood of ties
+        else {
+            __syncthreads();
+            if (threadIdx.x < K) s_flat[threadIdx.x] = 0ull;
+            __syncthreads();
+            if (threadIdx.x < ns) {
+                const uint64_t mine = s_surv[threadIdx.x];
+                int rank = 0;
+                for (int i = 0; i < ns; ++i) rank += (s_surv[i] > mine);
+                if (rank < K) s_flat[rank] = mine;
+            }
+            __syncthreads();
+        }
     }
-    __syncthreads();
+    if (!fast) {
+        // 1b (generic): each warp folds lists warp, warp+16, ... into a register-resident sorted
+        //     top-K (offer_lanes takes unsorted input), then a tree merge through shared memory.
+        __syncthreads();
+        WarpTopK<S> top;
+        top.init();
+        for (int p = warp; p < nparts; p += FIN_WARPS) {
+#pragma unroll
+            for (int s = 0; s < S; ++s) top.offer_lanes(partial[(size_t)p * K + s * 32 + lane], lane);
+        }
+        top.store(s_keys[warp], lane);
+        __syncthreads();
+#pragma unroll 1
+        for (int half = FIN_WARPS / 2; half >= 1; half >>= 1) {
+            if (warp < half) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) top.offer_lanes(s_keys[warp + half][s * 32 + lane], lane);
+                top.store(s_keys[warp], lane);
+            }
+            __syncthreads();
+        }
+    }
+    const uint64_t *s_cand = s_keys[0];
 
     // 2. canonical rescore, one warp per candidate
     const float *q = q_all + (size_t)qi * ORX_DIM;
@@ -112,20 +176,21 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
             continue;
         }
         const uint32_t row = key_row(key);
+        const double n2x = n2[row];                       // issued before the row itself: one DRAM round trip
+        const orx_id id = row_ids[row];
         const double dot = warp_canon_dot<T>(table + (size_t)row * ORX_DIM, q, lane);
         if (lane == 0) {
-            s_dist[c] = canon_dist(dot, n2[row], n2q);
-            s_hi[c] = row_ids[row].hi;
-            s_lo[c] = row_ids[row].lo;
+            s_dist[c] = canon_dist(dot, n2x, n2q);
+            s_hi[c] = id.hi;
+            s_lo[c] = id.lo;
+            atomicAdd(&s_valid, 1);
         }
     }
     __syncthreads();
 
     // 3. order by (distance ASC, NaN last, id ASC): rank by counting
     const int t = threadIdx.x;
-    int valid = 0;
-    for (int c = 0; c < K; ++c) valid += (s_cand[c] != 0ull);
-    const int count = min(k, valid);
+    const int count = min(k, s_valid);
     if (t < K && s_cand[t] != 0ull) {
         int rank = 0;
         const double d = s_dist[t];
@@ -178,7 +243,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                 flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
             }
         }
-        out_flags[qi] = flag;
+        out_flags[qi] = flag | (prep[qi].nonfinite ? 2 : 0) | (prep[qi].zero ? 4 : 0);
     }
 }
 
@@ -190,10 +255,12 @@ static void launch_finalize_t(const void *table, const double *n2, const orx_id 
     const T *tab = static_cast<const T *>(table);
     if (slots == 1)
         finalize_kernel<T, 1><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
-                                                          eps, out_ids, out_dist, out_counts, out_flags, floor);
+                                                          eps, out_ids, out_dist, out_counts, out_flags, floor,
+                                                          floor == nullptr);
     else
         finalize_kernel<T, 2><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
-                                                          eps, out_ids, out_dist, out_counts, out_flags, floor);
+                                                          eps, out_ids, out_dist, out_counts, out_flags, floor,
+                                                          floor == nullptr);
 }
 
 void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,
@@ -215,8 +282,9 @@ void launch_finalize(int dtype, const void *table, const double *n2, const orx_i
 constexpr int MERGE_MAX = 1024;
 
 __global__ void __launch_bounds__(256)
-merge_topk_kernel(int n_lists, int nq, int k, const orx_id *__restrict__ ids,
-                  const double *__restrict__ dist, const int *__restrict__ counts,
+merge_topk_kernel(int n_lists, int nq, int k, const char *__restrict__ ids_base,
+                  const char *__restrict__ dist_base, const char *__restrict__ counts_base,
+                  size_t ids_stride, size_t dist_stride, size_t counts_stride,
                   orx_id *__restrict__ out_ids, double *__restrict__ out_dist,
                   int *__restrict__ out_counts) {
     __shared__ double s_d[MERGE_MAX];
@@ -230,8 +298,12 @@ merge_topk_kernel(int n_lists, int nq, int k, const orx_id *__restrict__ ids,
     int mine = 0;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
         const int l = e / k, r = e % k;
-        const size_t src = ((size_t)l * nq + qi) * k + r;
-        const bool ok = r < counts[(size_t)l * nq + qi];
+        // list l lives at base + l * stride (bytes): separate arrays or one gathered block per rank
+        const orx_id *ids = reinterpret_cast<const orx_id *>(ids_base + (size_t)l * ids_stride);
+        const double *dist = reinterpret_cast<const double *>(dist_base + (size_t)l * dist_stride);
+        const int *counts = reinterpret_cast<const int *>(counts_base + (size_t)l * counts_stride);
+        const size_t src = (size_t)qi * k + r;
+        const bool ok = r < counts[qi];
         s_ok[e] = ok;
         s_d[e] = dist[src];
         s_hi[e] = ids[src].hi;
@@ -265,11 +337,16 @@ merge_topk_kernel(int n_lists, int nq, int k, const orx_id *__restrict__ ids,
 }
 
 void launch_merge_topk(int n_lists, int nq, int k, const orx_id *ids, const double *dist,
-                       const int *counts, orx_id *out_ids, double *out_dist, int *out_counts,
-                       cudaStream_t st) {
+                       const int *counts, size_t list_stride_bytes, orx_id *out_ids, double *out_dist,
+                       int *out_counts, cudaStream_t st) {
     if (nq <= 0) return;
-    merge_topk_kernel<<<nq, 256, 0, st>>>(n_lists, nq, k, ids, dist, counts, out_ids, out_dist,
-                                          out_counts);
+    const size_t si = list_stride_bytes ? list_stride_bytes : (size_t)nq * k * sizeof(orx_id);
+    const size_t sd = list_stride_bytes ? list_stride_bytes : (size_t)nq * k * sizeof(double);
+    const size_t sc = list_stride_bytes ? list_stride_bytes : (size_t)nq * sizeof(int);
+    merge_topk_kernel<<<nq, 256, 0, st>>>(n_lists, nq, k, reinterpret_cast<const char *>(ids),
+                                          reinterpret_cast<const char *>(dist),
+                                          reinterpret_cast<const char *>(counts), si, sd, sc, out_ids,
+                                          out_dist, out_counts);
 }
 
 // -------------------------------------------------- exhaustive fallback (rare path)

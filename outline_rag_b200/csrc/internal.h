@@ -24,16 +24,17 @@ struct QueryPrep {            // per query, written by prep_queries
 };
 
 // ---- finalize.cu
-void launch_prep_queries(const float *q, int nq, float *qhat, void *qhat_bf16,
+void launch_prep_queries(const float *q, int nq, float *q_copy, float *qhat, void *qhat_bf16,
                          QueryPrep *prep, cudaStream_t st);
 void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,
                      const float *q, const QueryPrep *prep, const uint64_t *partial, int nparts,
                      int slots, int nq, int k, uint32_t n_rows, double eps,
                      orx_id *out_ids, double *out_dist, int *out_counts, int *out_flags,
                      cudaStream_t st, const float *floor = nullptr);
+// list_stride_bytes == 0: three dense [n_lists][...] arrays; otherwise list l of each array is at +l*stride
 void launch_merge_topk(int n_lists, int nq, int k, const orx_id *ids, const double *dist,
-                       const int *counts, orx_id *out_ids, double *out_dist, int *out_counts,
-                       cudaStream_t st);
+                       const int *counts, size_t list_stride_bytes, orx_id *out_ids, double *out_dist,
+                       int *out_counts, cudaStream_t st);
 // exhaustive fallback: collect rows whose fast score may reach `cos_floor`, rescore, select
 void launch_collect(int dtype, const void *table, const float *scale, uint32_t n_rows,
                     const float *qhat, float fast_floor, int collect_all,

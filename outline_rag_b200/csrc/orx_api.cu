@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -95,7 +96,8 @@ struct PinBuf {
         if (p) cudaFreeHost(p);
         p = nullptr;
         n = 0;
-        cudaError_t e = cudaMallocHost(&p, want * sizeof(T));
+        // mapped: kernels write results / read small query batches directly over PCIe (no memcpy calls)
+        cudaError_t e = cudaHostAlloc(&p, want * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable);
         if (e == cudaSuccess) n = want;
         return e;
     }
@@ -254,7 +256,8 @@ struct SearchOut {          // where the results of query j go (device pointers)
     int *counts;
 };
 
-int exhaustive_query(orx_index *ix, int qi, int k, double dk, bool force_all, const SearchOut &out) {
+int exhaustive_query(orx_index *ix, const float *q_src, int qi, int k, double dk, bool force_all,
+                     const SearchOut &out) {
     // Collect every row that could sort at or before the current k-th candidate, rescore all of
     // them canonically, select the k best.  Always exact; cost grows with the number of near-ties.
     const uint32_t n_rows = (uint32_t)ix->n_live;
@@ -271,7 +274,7 @@ int exhaustive_query(orx_index *ix, int qi, int k, double dk, bool force_all, co
     CK(cudaMemsetAsync(ix->fb_count.p, 0, sizeof(uint32_t), ix->stream));
     orx::launch_collect(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qi * ORX_DIM, floor_f,
                         all ? 1 : 0, ix->fb_list.p, ix->fb_count.p, ix->stream);
-    orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, ix->q_dev.p + (size_t)qi * ORX_DIM,
+    orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)qi * ORX_DIM,
                              ix->prep.p + qi, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, ix->stream);
     orx::launch_select_list(ix->row_ids, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, k,
                             out.ids + (size_t)qi * k, out.dist + (size_t)qi * k, out.counts + qi, ix->stream);
@@ -281,7 +284,7 @@ int exhaustive_query(orx_index *ix, int qi, int k, double dk, bool force_all, co
     return ORX_OK;
 }
 
-int gemv_pass(orx_index *ix, int q0, int nq, int k, const SearchOut &out, int *flags_dev) {
+int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const SearchOut &out, int *flags) {
     const uint32_t n_rows = (uint32_t)ix->n_live;
     const int grid = orx::scan_gemv_grid(ix->device, n_rows);
     const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
@@ -295,18 +298,21 @@ int gemv_pass(orx_index *ix, int q0, int nq, int k, const SearchOut &out, int *f
         orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qa * ORX_DIM, m,
                               slots, ix->partial.p, grid, ix->stream);
         if (e0 && e1) CK(cudaEventRecord(e1, ix->stream));
-        orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, ix->q_dev.p + (size_t)qa * ORX_DIM,
+        orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)qa * ORX_DIM,
                              ix->prep.p + qa, ix->partial.p, grid, slots, m, k, n_rows, eps,
                              out.ids + (size_t)qa * k, out.dist + (size_t)qa * k, out.counts + qa,
-                             flags_dev + qa, ix->stream);
+                             flags + qa, ix->stream);
         ix->stats.kernel_launches += 2;
     }
     CK(cudaGetLastError());
     return ORX_OK;
 }
 
+constexpr int ZERO_COPY_MAX_Q = 16;     // query batches up to this size are read by the prep kernel over PCIe
+
 int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
                   int *out_counts) {
+    const auto t_begin = std::chrono::steady_clock::now();
     const bool q_on_dev = is_device_ptr(queries);
     const bool out_on_dev = is_device_ptr(out_ids);
     if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
@@ -315,115 +321,121 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
     const size_t nk = (size_t)nq * k;
     ix->scan_ev_used = 0;
 
-    CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
     CK(ix->qhat.ensure((size_t)nq * ORX_DIM));
     CK(ix->qhat16.ensure((size_t)nq * ORX_DIM));
     CK(ix->prep.ensure(nq));
-    CK(ix->res_flags.ensure(nq));
-    CK(ix->h_prep.ensure(nq));
     CK(ix->h_flags.ensure(nq));
-    CK(ix->h_ids.ensure(nk));
-    CK(ix->h_dist.ensure(nk));
-    CK(ix->h_counts.ensure(nq));
     if (!out_on_dev) {
-        CK(ix->res_ids.ensure(nk));
-        CK(ix->res_dist.ensure(nk));
-        CK(ix->res_counts.ensure(nq));
+        CK(ix->h_ids.ensure(nk));
+        CK(ix->h_dist.ensure(nk));
+        CK(ix->h_counts.ensure(nq));
     }
-    SearchOut out{out_on_dev ? out_ids : ix->res_ids.p, out_on_dev ? out_dist : ix->res_dist.p,
-                  out_on_dev ? out_counts : ix->res_counts.p};
+    // host-side results are written by the kernels straight into mapped pinned memory
+    SearchOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                  out_on_dev ? out_counts : ix->h_counts.p};
+    int *flags = ix->h_flags.p;
 
-    CK(cudaEventRecord(ix->ev[0], st));
+    // ---- query staging: q_src is what the rescoring kernels read (device memory)
+    const float *q_src = queries;
     if (q_on_dev) {
-        CK(cudaMemcpyAsync(ix->q_dev.p, queries, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        orx::launch_prep_queries(queries, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
     } else {
+        CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
         CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
         memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
-        CK(cudaMemcpyAsync(ix->q_dev.p, ix->h_q.p, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+        q_src = ix->q_dev.p;
+        if (nq <= ZERO_COPY_MAX_Q) {
+            orx::launch_prep_queries(ix->h_q.p, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+        } else {
+            CK(cudaMemcpyAsync(ix->q_dev.p, ix->h_q.p, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            orx::launch_prep_queries(ix->q_dev.p, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+        }
     }
-    orx::launch_prep_queries(ix->q_dev.p, nq, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
     ix->stats.kernel_launches += 1;
 
     const uint32_t n_rows = (uint32_t)ix->n_live;
     int path = 1;
-    CK(cudaEventRecord(ix->ev[1], st));
     if (n_rows == 0) {
-        CK(cudaMemsetAsync(out.ids, 0, nk * sizeof(orx_id), st));
-        CK(cudaMemsetAsync(out.dist, 0xFF, nk * sizeof(double), st));   // all-ones = NaN
-        CK(cudaMemsetAsync(out.counts, 0, nq * sizeof(int), st));
-        CK(cudaMemsetAsync(ix->res_flags.p, 0, nq * sizeof(int), st));
-    } else if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
+        // nothing to scan: only the pgvector input check matters
+        CK(ix->h_prep.ensure(nq));
+        CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int j = 0; j < nq; ++j)
+            if (ix->h_prep.p[j].nonfinite)
+                return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+        if (out_on_dev) {
+            CK(cudaMemsetAsync(out_ids, 0, nk * sizeof(orx_id), st));
+            CK(cudaMemsetAsync(out_dist, 0xFF, nk * sizeof(double), st));   // all-ones = NaN
+            CK(cudaMemsetAsync(out_counts, 0, nq * sizeof(int), st));
+            CK(cudaStreamSynchronize(st));
+        } else {
+            memset(out_ids, 0, nk * sizeof(orx_id));
+            memset(out_dist, 0xFF, nk * sizeof(double));
+            memset(out_counts, 0, nq * sizeof(int));
+        }
+        ix->stats.searches += 1;
+        ix->stats.queries += nq;
+        return ORX_OK;
+    }
+    if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
         path = 2;
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
-                                  ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
-                                  out.counts, ix->res_flags.p, st, &ix->stats.kernel_launches, e0, e1);
+                                  q_src, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
+                                  out.counts, flags, st, &ix->stats.kernel_launches, e0, e1);
         if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
     } else {
-        int rc = gemv_pass(ix, 0, nq, k, out, ix->res_flags.p);
+        int rc = gemv_pass(ix, q_src, 0, nq, k, out, flags);
         if (rc != ORX_OK) return rc;
     }
-    CK(cudaEventRecord(ix->ev[2], st));
+    CK(cudaStreamSynchronize(st));          // the only sync of the common path; flags are on the host now
 
-    // read back what the host must see to decide on fallbacks
-    CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ix->h_flags.p, ix->res_flags.p, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ix->h_dist.p, out.dist, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(ix->h_counts.p, out.counts, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (!out_on_dev) CK(cudaMemcpyAsync(ix->h_ids.p, out.ids, nk * sizeof(orx_id), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-
-    for (int j = 0; j < nq; ++j)
-        if (ix->h_prep.p[j].nonfinite)
-            return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
-
-    bool any_fb = false;
-    if (n_rows > 0) {
+    bool any_unproven = false;
+    for (int j = 0; j < nq; ++j) {
+        if (flags[j] & 2) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+        any_unproven |= (flags[j] & 1) != 0;
+    }
+    if (any_unproven) {
         // level 1: coarse tensor-core pass unproven -> exact fp32 scan for those queries
         if (path == 2) {
             for (int j = 0; j < nq; ++j) {
-                if (!ix->h_flags.p[j]) continue;
-                any_fb = true;
+                if (!(flags[j] & 1)) continue;
                 ix->stats.fallback_gemv += 1;
-                int rc = gemv_pass(ix, j, 1, k, out, ix->res_flags.p);
+                int rc = gemv_pass(ix, q_src, j, 1, k, out, flags);
                 if (rc != ORX_OK) return rc;
             }
-            if (any_fb) {
-                CK(cudaMemcpyAsync(ix->h_flags.p, ix->res_flags.p, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(ix->h_dist.p, out.dist, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
-                CK(cudaMemcpyAsync(ix->h_counts.p, out.counts, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-            }
+            CK(cudaStreamSynchronize(st));
         }
         // level 2: still unproven (dense near-ties, NaN rows, zero query) -> exhaustive collect
         for (int j = 0; j < nq; ++j) {
-            if (!ix->h_flags.p[j]) continue;
-            any_fb = true;
-            const int cnt = ix->h_counts.p[j];
-            const bool force_all = ix->h_prep.p[j].zero || cnt < k;
-            const double dk = cnt > 0 ? ix->h_dist.p[(size_t)j * k + cnt - 1] : NAN;
-            int rc = exhaustive_query(ix, j, k, dk, force_all, out);
+            if (!(flags[j] & 1)) continue;
+            int cnt = 0;
+            double dk = NAN;
+            if (out_on_dev) {
+                CK(cudaMemcpyAsync(&cnt, out.counts + j, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                if (cnt > 0) {
+                    CK(cudaMemcpyAsync(&dk, out.dist + (size_t)j * k + cnt - 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+                    CK(cudaStreamSynchronize(st));
+                }
+            } else {
+                cnt = out.counts[j];
+                if (cnt > 0) dk = out.dist[(size_t)j * k + cnt - 1];
+            }
+            const bool force_all = (flags[j] & 4) != 0 || cnt < k;
+            int rc = exhaustive_query(ix, q_src, j, k, dk, force_all, out);
             if (rc != ORX_OK) return rc;
         }
+        CK(cudaStreamSynchronize(st));
     }
-    CK(cudaEventRecord(ix->ev[3], st));
-    if (any_fb) {
-        if (!out_on_dev) {
-            CK(cudaMemcpyAsync(ix->h_ids.p, out.ids, nk * sizeof(orx_id), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ix->h_dist.p, out.dist, nk * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ix->h_counts.p, out.counts, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
-        }
-    }
-    CK(cudaStreamSynchronize(st));
     if (!out_on_dev) {
         memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
         memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
         memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
     }
-    float ms = 0.f;
     harvest_scan_events(ix);
-    if (cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[3]) == cudaSuccess) ix->stats.last_search_ms = ms;
-    cudaGetLastError();
+    ix->stats.last_search_ms =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     ix->stats.last_path = path;
     ix->stats.searches += 1;
     ix->stats.queries += nq;
@@ -717,7 +729,7 @@ int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids,
     const bool in_dev = is_device_ptr(ids), out_dev = is_device_ptr(out_ids);
     const size_t nin = (size_t)n_lists * nq * k, nout = (size_t)nq * k;
     if (in_dev && out_dev) {
-        orx::launch_merge_topk(n_lists, nq, k, ids, dist, counts, out_ids, out_dist, out_counts, st);
+        orx::launch_merge_topk(n_lists, nq, k, ids, dist, counts, 0, out_ids, out_dist, out_counts, st);
         ix->stats.kernel_launches += 1;
         CK(cudaGetLastError());
         return ORX_OK;
@@ -736,13 +748,30 @@ int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids,
     CK(cudaMemcpyAsync(d_ids, ids, nin * sizeof(orx_id), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_dist, dist, nin * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_cnt, counts, (size_t)n_lists * nq * sizeof(int), cudaMemcpyHostToDevice, st));
-    orx::launch_merge_topk(n_lists, nq, k, d_ids, d_dist, d_cnt, d_oids, d_odist, d_ocnt, st);
+    orx::launch_merge_topk(n_lists, nq, k, d_ids, d_dist, d_cnt, 0, d_oids, d_odist, d_ocnt, st);
     ix->stats.kernel_launches += 1;
     CK(cudaMemcpyAsync(out_ids, d_oids, nout * sizeof(orx_id), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_dist, d_odist, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_counts, d_ocnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     cudaFree(d_ids); cudaFree(d_dist); cudaFree(d_cnt); cudaFree(d_oids); cudaFree(d_odist); cudaFree(d_ocnt);
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int orx_merge_topk_strided(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids0, const double *dist0,
+                           const int *counts0, uint64_t list_stride_bytes, orx_id *out_ids, double *out_dist,
+                           int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n_lists < 1 || nq < 0 || k < 1 || k > ORX_MAX_K || (size_t)n_lists * k > 1024 || list_stride_bytes == 0)
+        return fail(ORX_ERR_INVALID, "bad merge shape (n_lists=%d, nq=%d, k=%d)", n_lists, nq, k);
+    if (nq == 0) return ORX_OK;
+    if (!ids0 || !dist0 || !counts0 || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    orx::launch_merge_topk(n_lists, nq, k, ids0, dist0, counts0, (size_t)list_stride_bytes, out_ids, out_dist,
+                           out_counts, ix->stream);
+    ix->stats.kernel_launches += 1;
     CK(cudaGetLastError());
     return ORX_OK;
 }

@@ -66,19 +66,25 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
         }
     }
 
-    // per-CTA merge: warp 0 folds the other warps' sorted lists into its own
+    // per-CTA merge by counting: the 8 warp lists hold 8*K distinct keys (0 = empty); a key's rank
+    // is the number of larger keys, ranks < K are the CTA's sorted top-K.
     top.store(s_keys[warp], lane);
     __syncthreads();
-    if (warp == 0) {
-        for (int w = 1; w < SCAN_WARPS; ++w) {
+    const uint64_t *all = &s_keys[0][0];
+    constexpr int TOTAL = SCAN_WARPS * K;
+    int nonzero = 0;
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-                // lists are sorted: once a slot's best key fails, later slots fail too
-                top.offer_lanes(s_keys[w][s * 32 + lane], lane);
-            }
-        }
-        top.store(partial, lane);
+    for (int h = 0; h < TOTAL / SCAN_THREADS; ++h) {
+        const uint64_t mine = all[threadIdx.x + h * SCAN_THREADS];
+        nonzero += (mine != 0ull);
+        if (mine == 0ull) continue;
+        int rank = 0;
+#pragma unroll 8
+        for (int i = 0; i < TOTAL; ++i) rank += (all[i] > mine);
+        if (rank < K) partial[rank] = mine;
     }
+    const int nnz = __syncthreads_count(nonzero != 0) + (TOTAL > SCAN_THREADS ? __syncthreads_count(nonzero == 2) : 0);
+    if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
 }
 
 int scan_gemv_grid(int device, uint32_t n_rows) {

@@ -196,6 +196,24 @@ class Index:
                              C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
         return ids, dist, cnt
 
+    def search_into(self, queries, k: int, ids_out, dist_out, counts_out) -> None:
+        """`search` of a float32 CUDA tensor writing into caller-owned CUDA tensors (views of one
+        result block in the row-sharded path: no allocation, no packing kernels)."""
+        q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+        check(lib.orx_search(self._h, C.c_void_p(q.data_ptr()), q.shape[0], q.shape[1], int(k),
+                             C.c_void_p(ids_out.data_ptr()), C.c_void_p(dist_out.data_ptr()),
+                             C.c_void_p(counts_out.data_ptr())))
+
+    def merge_blocks(self, gathered, n_lists: int, nq: int, k: int, stride_bytes: int, ids_out, dist_out,
+                     counts_out) -> None:
+        """Merge the per-rank result blocks an all_gather left in `gathered` (int64 CUDA tensor; each
+        block = ids [nq,k,2] | distance bits [nq,k] | counts int32 [nq]) into the global top-k."""
+        base = gathered.data_ptr()
+        check(lib.orx_merge_topk_strided(self._h, int(n_lists), int(nq), int(k), C.c_void_p(base),
+                                         C.c_void_p(base + nq * k * 16), C.c_void_p(base + nq * k * 24),
+                                         int(stride_bytes), C.c_void_p(ids_out.data_ptr()),
+                                         C.c_void_p(dist_out.data_ptr()), C.c_void_p(counts_out.data_ptr())))
+
     def merge_topk(self, ids, dist, counts, k: int):
         """Merge ``[n_lists, nq, k]`` shard results (NumPy or CUDA tensors) into the global top-k."""
         if _is_cuda_tensor(ids):

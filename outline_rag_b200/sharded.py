@@ -3,8 +3,9 @@
 SURVEY.md 8(e): rows are independent, so the table is partitioned by
 ``shard = mix64(id) mod G`` (balanced under upsert/delete churn); every rank receives the
 full query batch, scans its shard, and only the k candidates per query are exchanged:
-ONE ``all_gather`` of a packed ``[nq, 3k+1]`` int64 block per rank (144..147 KB at
-k=12), then the on-device merge (``orx_merge_topk``) with the same ordering contract
+ONE ``all_gather`` of a result block per rank (ids | distance bits | counts, 292 B per
+query at k=12), then the on-device merge (``orx_merge_topk_strided``, reading the gathered
+buffer in place) with the same ordering contract
 (distance ASC, NaN last, id ASC).  Distances are the canonical binary64 values, so shard
 results are comparable bit for bit and the merged answer equals the single-GPU answer.
 
@@ -68,6 +69,28 @@ class ShardedIndex:
         self.local = local_index if local_index is not None else Index(dtype, capacity_per_rank, device)
         self._merge = merge_fn if merge_fn is not None else self.local.merge_topk
         self.gather_launches = 0
+        self._plans = {}
+
+    def _plan(self, nq: int, k: int, device):
+        """Reusable device buffers for one (nq, k): my result block (the scan's output arrays are
+        views of it), the gathered blocks of all ranks, and the merged result."""
+        key = (nq, k, str(device))
+        p = self._plans.get(key)
+        if p is None:
+            words = nq * k * 3 + (nq + 1) // 2                       # ids 2nk | dist nk | counts ceil(nq/2)
+            block = torch.zeros(words, dtype=torch.int64, device=device)
+            p = {
+                "words": words, "block": block,
+                "ids": block[:2 * nq * k].view(nq, k, 2),
+                "dist": block[2 * nq * k:3 * nq * k].view(torch.float64).view(nq, k),
+                "cnt": block[3 * nq * k:].view(torch.int32)[:nq],
+                "gathered": torch.zeros(self.world * words, dtype=torch.int64, device=device),
+                "out_ids": torch.zeros((nq, k, 2), dtype=torch.int64, device=device),
+                "out_dist": torch.zeros((nq, k), dtype=torch.float64, device=device),
+                "out_cnt": torch.zeros((nq,), dtype=torch.int32, device=device),
+            }
+            self._plans[key] = p
+        return p
 
     def __len__(self) -> int:
         return len(self.local)
@@ -106,7 +129,18 @@ class ShardedIndex:
     # ------------------------------------------------------------------- reads
     def search(self, queries, k: int = 12):
         """Global top-k on every rank.  ``queries`` is identical on all ranks (CUDA tensor for the
-        NCCL path; NumPy for the CPU/gloo test path)."""
+        NCCL path; NumPy for the CPU/gloo test path).  On the CUDA path the returned tensors are
+        reusable per-(nq, k) buffers: they are overwritten by the next search of the same shape."""
+        if self.world > 1 and isinstance(queries, torch.Tensor) and queries.is_cuda and hasattr(self.local, "search_into"):
+            q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+            nq = q.shape[0]
+            p = self._plan(nq, k, q.device)
+            self.local.search_into(q, k, p["ids"], p["dist"], p["cnt"])
+            dist.all_gather_into_tensor(p["gathered"], p["block"], group=self.group)
+            self.gather_launches += 1
+            self.local.merge_blocks(p["gathered"], self.world, nq, k, p["words"] * 8, p["out_ids"], p["out_dist"],
+                                    p["out_cnt"])
+            return p["out_ids"], p["out_dist"], p["out_cnt"]
         ids, dist_, cnt = self.local.search(queries, k)
         if self.world == 1:
             return ids, dist_, cnt

@@ -413,3 +413,38 @@ def test_tcgen05_duplicates_overflow_falls_back(Index, synth100k):
         _check_exact(ix, X, ids, Q)
         st = ix.stats()
     assert st["fallback_gemv"] >= 1 and st["fallback_exhaustive"] >= 1
+
+
+def test_gathered_block_merge_equals_single_table(Index, small_table):
+    """The NCCL path's data flow on one GPU: every shard searches INTO views of its result block,
+    the blocks are concatenated the way all_gather_into_tensor leaves them, and
+    orx_merge_topk_strided reads the gathered buffer in place."""
+    import torch
+    from outline_rag_b200.sharded import ShardedIndex, shard_of
+    X, Q, _ = small_table
+    n, G, nq = 6000, 4, 7
+    ids = _ids(n)
+    owner = shard_of(ids, G)
+    qd = torch.from_numpy(Q[:nq]).cuda()
+    shards = [Index("fp32") for _ in range(G)]
+    try:
+        host = ShardedIndex(local_index=shards[0])
+        host.world = G                                   # lay the plan out for G ranks
+        p = host._plan(nq, K, qd.device)
+        blocks = []
+        for s, ix in enumerate(shards):
+            ix.upsert(ids[owner == s], X[:n][owner == s])
+            ix.search_into(qd, K, p["ids"], p["dist"], p["cnt"])
+            blocks.append(p["block"].clone())
+        p["gathered"].copy_(torch.cat(blocks))
+        shards[0].merge_blocks(p["gathered"], G, nq, K, p["words"] * 8, p["out_ids"], p["out_dist"], p["out_cnt"])
+        torch.cuda.synchronize()
+        m_ids = p["out_ids"].cpu().numpy().view(np.uint64)
+        m_d = p["out_dist"].cpu().numpy()
+        assert (p["out_cnt"].cpu().numpy() == K).all()
+    finally:
+        for ix in shards:
+            ix.close()
+    for i in range(nq):
+        w_ids, w_d = O.topk_exact(X[:n], ids, Q[i], K)
+        assert np.array_equal(m_ids[i], w_ids) and np.array_equal(m_d[i].view(np.uint64), w_d.view(np.uint64))
