@@ -52,6 +52,11 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=200_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--verify", type=int, default=4, help="queries re-checked on the host against the oracle")
+    ap.add_argument("--recall-queries", type=int, default=0,
+                    help="bf16 tables: also build an fp32 twin and report recall@12 of the bf16 ids vs the fp32 ids")
+    ap.add_argument("--mixed", action="store_true",
+                    help="config 5: REFRESH_BATCH_SIZE=50-doc delete+upsert between every 100 single-query searches")
+    ap.add_argument("--mixed-rounds", type=int, default=20)
     return ap.parse_args()
 
 
@@ -191,7 +196,7 @@ def run_reference(a):
 
 
 # ------------------------------------------------------------------ GPU arm
-def build_table(ix_upsert, device, rows, rank, world, chunk=262_144):
+def build_table(ix_upsert, device, rows, rank, world, chunk=262_144, also=None):
     """Generate the synthetic table in HBM chunk by chunk and upsert the rows this rank owns."""
     import torch
     from outline_rag_b200 import synth_rows_device
@@ -211,9 +216,13 @@ def build_table(ix_upsert, device, rows, rank, world, chunk=262_144):
                 continue
             v = buf[:m].index_select(0, torch.from_numpy(sel).to(buf.device))
             ix_upsert(ids[sel], v)
+            if also is not None:
+                also(ids[sel], v)
             owned += sel.size
         else:
             ix_upsert(ids, buf[:m])
+            if also is not None:
+                also(ids, buf[:m])
             owned += m
     torch.cuda.synchronize(device)
     del buf
@@ -241,8 +250,12 @@ def run_ours(a):
     sh = ShardedIndex(a.dtype, per_rank_cap if world > 1 else a.rows, local)
     ix = sh.local
     ix.use_torch_stream()
+    twin = None
+    if a.recall_queries > 0 and a.dtype == "bf16":       # fp32 twin of the same rows, for recall@12
+        twin = ShardedIndex("fp32", per_rank_cap if world > 1 else a.rows, local)
+        twin.local.use_torch_stream()
     t0 = time.perf_counter()
-    owned = build_table(ix.upsert, local, a.rows, rank, world)
+    owned = build_table(ix.upsert, local, a.rows, rank, world, also=twin.local.upsert if twin is not None else None)
     build_s = time.perf_counter() - t0
     assert len(ix) == owned
 
@@ -295,6 +308,20 @@ def run_ours(a):
     total_ms, lat, s0, s1 = timed(step_device, a.steps, max(a.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms, e2e_lat, _, _ = timed(step_host, a.steps, max(a.warmup, 3))
+
+    # bf16 mode: recall@12 against the fp32 engine on the same rows (collective; outside the timed region)
+    recall = None
+    if twin is not None:
+        nrq = min(a.recall_queries, Qh.shape[0])
+        hits = 0
+        for j in range(0, nrq, 64):
+            qd = Qd[j:min(j + 64, nrq)]
+            got = sh.search(qd, K)[0].cpu().numpy()[:, :, 1]
+            want = twin.search(qd, K)[0].cpu().numpy()[:, :, 1]
+            hits += sum(len(set(g.tolist()) & set(w.tolist())) for g, w in zip(got, want))
+            if os.environ.get("ORX_BENCH_DEBUG") and j == 0 and rank == 0:
+                print("recall debug", got[0], want[0], len(twin), len(sh), file=sys.stderr)
+        recall = {"recall_at_12_vs_fp32": hits / (nrq * K), "queries": nrq}
 
     # correctness spot check against the oracle on host-regenerated rows (never inside the timed region)
     verify = {}
@@ -359,7 +386,7 @@ def run_ours(a):
         "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4,
                 "d2h_bytes_per_step": B * K * (16 + 8) + B * 4, "p50_ms": float(np.median(e2e_lat) * 1e3)},
         "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
-        "roofline": roof, "clocks": clocks, "verify": verify,
+        "roofline": roof, "clocks": clocks, "verify": verify, "recall": recall,
         "fallbacks": {"gemv": int(s1["fallback_gemv"] - s0["fallback_gemv"]),
                       "exhaustive": int(s1["fallback_exhaustive"] - s0["fallback_exhaustive"])},
     }
@@ -371,10 +398,103 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_mixed(a):
+    """BASELINE.json configs[4]: the webhook refresh (reference app/rag.py:216-235: look up the old chunk
+    ids of REFRESH_BATCH_SIZE=50 docs, `adelete` them, `aadd_documents` the re-chunked rows) interleaved
+    with top-12 queries.  One round = delete(~1000 ids) + upsert(~1000 rows, host buffers) + 100 searches."""
+    import torch
+    import outline_rag_b200 as orx
+    from outline_rag_b200.synth import Synth, default_centres, doc_chunk_counts
+    torch.cuda.set_device(0)
+    ix = orx.Index(a.dtype, a.rows + 200_000, 0)
+    ix.use_torch_stream()
+    build_table(ix.upsert, 0, a.rows, 0, 1)
+    syn = Synth(default_centres(a.rows))
+    Qh, _ = syn.queries(128, a.rows)
+    # documents = consecutive runs of 8..40 chunk ids (mean ~20) over the initial table
+    counts = doc_chunk_counts(a.rows // 16)
+    starts = np.concatenate([[0], np.cumsum(counts)])
+    n_docs = int(np.searchsorted(starts, a.rows, side="right") - 1)
+    rng = np.random.default_rng(20261020)
+    order = rng.permutation(n_docs)
+    docs_per_batch, searches_per_round = orx.REFRESH_BATCH_SIZE, 100
+    next_id = a.rows
+    rounds = []
+    for r in range(a.mixed_rounds + 2):
+        docs = order[r * docs_per_batch:(r + 1) * docs_per_batch]
+        old_ids = np.concatenate([np.arange(starts[d], starts[d + 1]) for d in docs]).astype(np.uint64)
+        n_new = int(counts[docs].sum())                       # re-chunked: same sizes, new uuids, new embeddings
+        new_ids = np.arange(next_id, next_id + n_new, dtype=np.uint64)
+        new_vecs = syn.rows(new_ids)                          # stands in for the remote embedding service
+        next_id += n_new
+        rounds.append((old_ids, new_ids, new_vecs))
+
+    def search_loop(n, lat):
+        for i in range(n):
+            t = time.perf_counter()
+            ix.search(Qh[i % 128:i % 128 + 1], K)
+            lat.append(time.perf_counter() - t)
+
+    lat_idle = []
+    search_loop(200, [])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    search_loop(a.mixed_rounds * searches_per_round, lat_idle)
+    idle_s = time.perf_counter() - t0
+
+    lat_mixed, t_del, t_up = [], [], []
+    s0 = ix.stats()
+    for old_ids, new_ids, new_vecs in rounds[:2]:             # warm-up rounds (buffers, maps)
+        ix.delete(old_ids); ix.upsert(new_ids, new_vecs); search_loop(10, [])
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n_rows_written = 0
+    for old_ids, new_ids, new_vecs in rounds[2:]:
+        t = time.perf_counter(); removed = ix.delete(old_ids); t_del.append(time.perf_counter() - t)
+        assert removed == len(old_ids)
+        t = time.perf_counter(); ix.upsert(new_ids, new_vecs); t_up.append(time.perf_counter() - t)
+        n_rows_written += len(new_ids)
+        search_loop(searches_per_round, lat_mixed)
+    torch.cuda.synchronize()
+    mixed_s = time.perf_counter() - t0
+    s1 = ix.stats()
+    assert len(ix) == a.rows
+    # deleted chunks never come back, new ones are searchable
+    probe = rounds[-1][2][:4]
+    got = ix.search(probe, 1)[0][:, 0, 1]
+    ok = bool((got == rounds[-1][1][:4]).all())
+    n_search = a.mixed_rounds * searches_per_round
+    line = {"metric": METRIC + "_mixed", "value": n_search / mixed_s, "unit": UNIT, "n_gpus": 1,
+            "steps": n_search, "warmup": 220, "ms_per_step": mixed_s / n_search * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "bf16",
+            "data": "synthetic",
+            "config": {"workload": f"mixed: per round delete+upsert of {docs_per_batch} docs (~{n_rows_written // a.mixed_rounds} "
+                                   f"rows) then {searches_per_round} single-query top-{K} searches, {a.rows}x{DIM} {a.dtype}",
+                       "rounds": a.mixed_rounds},
+            "search_only": {"qps": n_search / idle_s, "p50_ms": float(np.median(lat_idle) * 1e3),
+                            "p99_ms": float(np.percentile(lat_idle, 99) * 1e3)},
+            "with_writer": {"qps": n_search / mixed_s, "p50_ms": float(np.median(lat_mixed) * 1e3),
+                            "p99_ms": float(np.percentile(lat_mixed, 99) * 1e3),
+                            "delete_ms_p50": float(np.median(t_del) * 1e3), "upsert_ms_p50": float(np.median(t_up) * 1e3),
+                            "max_ms": float(np.max(lat_mixed) * 1e3), "top5_ms": [float(x * 1e3) for x in np.sort(lat_mixed)[-5:]],
+                            "delete_ms_mean": float(np.mean(t_del) * 1e3), "upsert_ms_mean": float(np.mean(t_up) * 1e3),
+                            "upsert_ms_all": [round(float(x * 1e3), 2) for x in t_up],
+                            "fallbacks": {"gemv": int(s1["fallback_gemv"] - s0["fallback_gemv"]),
+                                          "exhaustive": int(s1["fallback_exhaustive"] - s0["fallback_exhaustive"])},
+                            "rows_moved_by_compaction": int(s1["rows_moved"] - s0["rows_moved"])},
+            "e2e": {"value": n_search / mixed_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4 + n_rows_written * DIM * 4 // n_search,
+                    "d2h_bytes_per_step": K * 24 + 4},
+            "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
+            "verify": {"new_rows_searchable_and_table_size_constant": ok}}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     a = parse_args()
     if a.impl == "reference":
         run_reference(a)
+    elif a.mixed:
+        run_mixed(a)
     else:
         run_ours(a)
 

@@ -68,12 +68,23 @@ size_t elem_size(int dtype) { return dtype == ORX_DTYPE_F32 ? 4 : 2; }
 constexpr uint64_t STAGE_ROWS = 65536;   // 256 MB fp32 staging chunk for host uploads
 constexpr int GEMV_QCHUNK = 64;          // queries per gemv launch (partial-list scratch bound)
 
+// Scratch buffers grow geometrically (and never below 64 KB): re-allocating device or pinned memory
+// synchronises the device and costs up to tens of ms, which showed up as latency spikes in the
+// interleaved upsert / search workload when a refresh batch was a few rows larger than any before.
+template <typename T>
+size_t grown(size_t have, size_t want) {
+    size_t n = std::max(want, have * 2);
+    const size_t floor_elems = (64 * 1024 + sizeof(T) - 1) / sizeof(T);
+    return std::max(n, floor_elems);
+}
+
 template <typename T>
 struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
     cudaError_t ensure(size_t want) {
         if (want <= n) return cudaSuccess;
+        want = grown<T>(n, want);
         if (p) cudaFree(p);
         p = nullptr;
         n = 0;
@@ -93,6 +104,7 @@ struct PinBuf {
     size_t n = 0;
     cudaError_t ensure(size_t want) {
         if (want <= n) return cudaSuccess;
+        want = grown<T>(n, want);
         if (p) cudaFreeHost(p);
         p = nullptr;
         n = 0;
