@@ -277,8 +277,8 @@ def run_ours(a):
 
     def step_host(i):
         j = (i % n_batches) * B
-        if world == 1:
-            return ix.search(Qpin[j:j + B].numpy(), K)
+        if world == 1 or sh.exchange == "p2p":
+            return sh.search(Qpin[j:j + B].numpy(), K)          # host buffers straight through the C-ABI
         out = sh.search(Qpin[j:j + B].cuda(non_blocking=True), K)
         return tuple(t.cpu() for t in out)
 
@@ -379,7 +379,7 @@ def run_ours(a):
         "ms_per_step": total_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32" if a.dtype == "fp32" else "bf16", "data": "synthetic",
         "config": {"workload": workload_name(a), "rows": a.rows, "rows_per_gpu": owned, "dim": DIM, "k": K,
-                   "batch": B, "parallelism": f"row-shard x{world}", "l2": "table >> 126 MB L2 (no flush needed)"
+                   "batch": B, "parallelism": f"row-shard x{world}", "exchange": sh.exchange, "l2": "table >> 126 MB L2 (no flush needed)"
                    if bytes_per_launch > 512e6 else "table fits L2: numbers are L2-resident",
                    "table_build_s": round(build_s, 2)},
         "p50_ms": float(np.median(lat) * 1e3), "p99_ms": float(np.percentile(lat, 99) * 1e3),

@@ -118,6 +118,21 @@ int orx_merge_topk_strided(orx_index *idx, int n_lists, int nq, int k,
                            uint64_t list_stride_bytes,
                            orx_id *out_ids, double *out_dist, int *out_counts);
 
+/* ---- row-sharded search over NVLink peer memory (one process per GPU) ----------
+ * Setup, once: every rank calls orx_shard_export (allocates its gather buffer, returns a CUDA IPC
+ * handle of ORX_IPC_HANDLE_BYTES bytes), the handles are exchanged out of band (torch.distributed
+ * all_gather in outline_rag_b200/sharded.py), then every rank calls orx_shard_connect with all
+ * `world` handles in rank order.
+ * orx_search_sharded is COLLECTIVE: every rank calls it with the same queries, nq and k.  Each GPU
+ * scans its shard, pushes its k candidates per query into every peer's gather buffer with P2P
+ * stores, and merges what arrives; every rank receives the global top-k (same layout and ordering
+ * as orx_search).  Replaces the same SQL as orx_search, for a table partitioned by row. */
+#define ORX_IPC_HANDLE_BYTES 64
+int orx_shard_export(orx_index *idx, int world, int rank, void *handle_out);
+int orx_shard_connect(orx_index *idx, const void *handles, int n_handles);
+int orx_search_sharded(orx_index *idx, const float *queries, int nq, int dim, int k,
+                       orx_id *out_ids, double *out_dist, int *out_counts);
+
 /* Read back stored rows (as fp32) by id -- snapshot / debugging / tests.
  * out_vecs [n, dim] host; out_found [n] host (1/0). */
 int orx_fetch(orx_index *idx, const orx_id *ids, uint64_t n, float *out_vecs, int *out_found);

@@ -17,6 +17,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ORX_DIM = 1024
 ORX_MAX_K = 32
+ORX_IPC_HANDLE_BYTES = 64
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
 
@@ -79,6 +80,9 @@ SIGNATURES = {
     "orx_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "orx_merge_topk": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "orx_merge_topk_strided": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
+    "orx_shard_export": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "orx_shard_connect": (C.c_int, [_vp, _vp, C.c_int]),
+    "orx_search_sharded": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "orx_fetch": (C.c_int, [_vp, _vp, C.c_uint64, _vp, _vp]),
     "orx_synth_rows": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp]),
     "orx_last_error": (C.c_char_p, []),

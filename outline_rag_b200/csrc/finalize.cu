@@ -56,6 +56,14 @@ void launch_prep_queries(const float *q, int nq, float *q_copy, float *qhat, voi
                                                       static_cast<__nv_bfloat16 *>(qhat_bf16), prep);
 }
 
+__global__ void flags_from_prep_kernel(const QueryPrep *__restrict__ prep, int nq, int *__restrict__ flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nq) flags[j] = (prep[j].nonfinite ? 2 : 0) | (prep[j].zero ? 4 : 0);
+}
+void launch_flags_from_prep(const QueryPrep *prep, int nq, int *flags, cudaStream_t st) {
+    if (nq > 0) flags_from_prep_kernel<<<(nq + 127) / 128, 128, 0, st>>>(prep, nq, flags);
+}
+
 // ------------------------------------------------------------------- finalize
 // One CTA of 16 warps per query (512 threads: the binary64 rescore needs ~100 registers).
 //   1. every warp folds its share of the per-CTA candidate lists into a register-resident sorted

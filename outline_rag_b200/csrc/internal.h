@@ -46,6 +46,16 @@ void launch_select_list(const orx_id *row_ids, const uint32_t *list, const uint3
                         const double *dist, int k, orx_id *out_ids, double *out_dist,
                         int *out_count, cudaStream_t st);
 
+void launch_flags_from_prep(const QueryPrep *prep, int nq, int *flags, cudaStream_t st);
+
+// ---- exchange.cu (row-sharded search over NVLink peer memory)
+void launch_publish(const void *my_slot, void *const *peer_slot, uint32_t *const *peer_flag, int world,
+                    size_t bytes, uint32_t seq, cudaStream_t st);
+void launch_merge_wait(int world, int rank, int nq, int k, const void *set_base, size_t slot_stride,
+                       size_t dist_off, size_t counts_off, size_t flags_off, const uint32_t *arrival,
+                       int arrival_stride_words, uint32_t seq, orx_id *out_ids, double *out_dist,
+                       int *out_counts, int *flags_any, int *flags_mine, int *redo, cudaStream_t st);
+
 // ---- scan_gemv.cu
 int scan_gemv_grid(int device, uint32_t n_rows);
 void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t n_rows,

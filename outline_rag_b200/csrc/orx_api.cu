@@ -122,6 +122,24 @@ struct PinBuf {
 
 }  // namespace
 
+constexpr int XQ_MAX = 1024;                         // queries per exchange round (larger batches are chunked)
+constexpr size_t XFLAG_STRIDE = 128;                 // one arrival word per 128 bytes
+
+struct Exchange {   // peer-memory exchange state of one rank (orx_shard_*)
+    int world = 0, rank = 0;
+    size_t slot_bytes = 0;                           // capacity of one slot
+    size_t set_bytes = 0;                            // world slots
+    size_t flags_off = 0;                            // offset of the arrival words (2 sets x world x 128 B)
+    size_t total_bytes = 0;
+    char *base = nullptr;                            // my buffer
+    std::vector<char *> peer_base;                   // every rank's buffer as mapped in this process
+    void **d_peer_slot[2] = {nullptr, nullptr};      // device arrays [world]: MY slot inside peer g's set s
+    uint32_t **d_peer_flag[2] = {nullptr, nullptr};  // device arrays [world]: MY arrival word on peer g, set s
+    uint32_t seq = 0;
+    bool connected = false;
+};
+
+
 struct orx_index {
     int device = 0;
     int dtype = ORX_DTYPE_F32;
@@ -152,7 +170,8 @@ struct orx_index {
     PinBuf<orx::QueryPrep> h_prep;
     PinBuf<orx_id> h_ids;
     PinBuf<double> h_dist;
-    PinBuf<int> h_counts, h_flags;
+    PinBuf<int> h_counts, h_flags, h_myflags, h_redo;
+    struct Exchange *xchg = nullptr;     // peer-memory exchange of the row-sharded search (orx_shard_*)
     // exhaustive fallback scratch
     DevBuf<uint32_t> fb_list, fb_count;
     DevBuf<double> fb_dist;
@@ -322,10 +341,92 @@ int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const Se
 
 constexpr int ZERO_COPY_MAX_Q = 16;     // query batches up to this size are read by the prep kernel over PCIe
 
+// ---- query staging: *q_src is what the rescoring kernels read (device memory); launches prep
+int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_src) {
+    cudaStream_t st = ix->stream;
+    CK(ix->qhat.ensure((size_t)nq * ORX_DIM));
+    CK(ix->qhat16.ensure((size_t)nq * ORX_DIM));
+    CK(ix->prep.ensure(nq));
+    if (is_device_ptr(queries)) {
+        *q_src = queries;
+        orx::launch_prep_queries(queries, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+    } else {
+        CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
+        CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
+        memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
+        *q_src = ix->q_dev.p;
+        if (nq <= ZERO_COPY_MAX_Q) {
+            orx::launch_prep_queries(ix->h_q.p, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+        } else {
+            CK(cudaMemcpyAsync(ix->q_dev.p, ix->h_q.p, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            orx::launch_prep_queries(ix->q_dev.p, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+        }
+    }
+    ix->stats.kernel_launches += 1;
+    return ORX_OK;
+}
+
+// ---- the scan + finalize of all nq queries (tcgen05 for batches, GEMV otherwise); *path = 1 / 2
+int scan_pass(orx_index *ix, const float *q_src, int nq, int k, const SearchOut &out, int *flags, int *path) {
+    const uint32_t n_rows = (uint32_t)ix->n_live;
+    if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
+        *path = 2;
+        cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
+        int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
+                                  q_src, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
+                                  out.counts, flags, ix->stream, &ix->stats.kernel_launches, e0, e1);
+        if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
+        return ORX_OK;
+    }
+    *path = 1;
+    return gemv_pass(ix, q_src, 0, nq, k, out, flags);
+}
+
+// ---- re-answer the queries whose flag bit 0 (unproven) is set.  `flags` is where the kernels
+//      write (device or mapped host); hflags is a host-readable copy, refreshed here as needed.
+int resolve_unproven(orx_index *ix, const float *q_src, int nq, int k, const SearchOut &out, int *flags,
+                     int *hflags, int path, bool host_readable) {
+    cudaStream_t st = ix->stream;
+    // level 1: coarse tensor-core pass unproven -> exact fp32 scan for those queries
+    if (path == 2) {
+        for (int j = 0; j < nq; ++j) {
+            if (!(hflags[j] & 1)) continue;
+            ix->stats.fallback_gemv += 1;
+            int rc = gemv_pass(ix, q_src, j, 1, k, out, flags);
+            if (rc != ORX_OK) return rc;
+        }
+        if (!host_readable) CK(cudaMemcpyAsync(hflags, flags, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    // level 2: still unproven (dense near-ties, NaN rows, zero query) -> exhaustive collect
+    for (int j = 0; j < nq; ++j) {
+        if (!(hflags[j] & 1)) continue;
+        int cnt = 0;
+        double dk = NAN;
+        if (!host_readable) {
+            CK(cudaMemcpyAsync(&cnt, out.counts + j, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (cnt > 0) {
+                CK(cudaMemcpyAsync(&dk, out.dist + (size_t)j * k + cnt - 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+        } else {
+            cnt = out.counts[j];
+            if (cnt > 0) dk = out.dist[(size_t)j * k + cnt - 1];
+        }
+        const bool force_all = (hflags[j] & 4) != 0 || cnt < k;
+        int rc = exhaustive_query(ix, q_src, j, k, dk, force_all, out);
+        if (rc != ORX_OK) return rc;
+        hflags[j] &= ~1;
+        if (!host_readable) CK(cudaMemsetAsync(flags + j, 0, sizeof(int), st));   // proven now (exhaustive is exact)
+    }
+    CK(cudaStreamSynchronize(st));
+    return ORX_OK;
+}
+
 int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
                   int *out_counts) {
     const auto t_begin = std::chrono::steady_clock::now();
-    const bool q_on_dev = is_device_ptr(queries);
     const bool out_on_dev = is_device_ptr(out_ids);
     if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
         return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
@@ -333,9 +434,6 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
     const size_t nk = (size_t)nq * k;
     ix->scan_ev_used = 0;
 
-    CK(ix->qhat.ensure((size_t)nq * ORX_DIM));
-    CK(ix->qhat16.ensure((size_t)nq * ORX_DIM));
-    CK(ix->prep.ensure(nq));
     CK(ix->h_flags.ensure(nq));
     if (!out_on_dev) {
         CK(ix->h_ids.ensure(nk));
@@ -347,23 +445,9 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
                   out_on_dev ? out_counts : ix->h_counts.p};
     int *flags = ix->h_flags.p;
 
-    // ---- query staging: q_src is what the rescoring kernels read (device memory)
-    const float *q_src = queries;
-    if (q_on_dev) {
-        orx::launch_prep_queries(queries, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
-    } else {
-        CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
-        CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
-        memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
-        q_src = ix->q_dev.p;
-        if (nq <= ZERO_COPY_MAX_Q) {
-            orx::launch_prep_queries(ix->h_q.p, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
-        } else {
-            CK(cudaMemcpyAsync(ix->q_dev.p, ix->h_q.p, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
-            orx::launch_prep_queries(ix->q_dev.p, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
-        }
-    }
-    ix->stats.kernel_launches += 1;
+    const float *q_src = nullptr;
+    int rc = stage_queries(ix, queries, nq, &q_src);
+    if (rc != ORX_OK) return rc;
 
     const uint32_t n_rows = (uint32_t)ix->n_live;
     int path = 1;
@@ -389,17 +473,8 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         ix->stats.queries += nq;
         return ORX_OK;
     }
-    if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
-        path = 2;
-        cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
-        int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
-                                  q_src, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
-                                  out.counts, flags, st, &ix->stats.kernel_launches, e0, e1);
-        if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
-    } else {
-        int rc = gemv_pass(ix, q_src, 0, nq, k, out, flags);
-        if (rc != ORX_OK) return rc;
-    }
+    rc = scan_pass(ix, q_src, nq, k, out, flags, &path);
+    if (rc != ORX_OK) return rc;
     CK(cudaStreamSynchronize(st));          // the only sync of the common path; flags are on the host now
 
     bool any_unproven = false;
@@ -408,37 +483,122 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         any_unproven |= (flags[j] & 1) != 0;
     }
     if (any_unproven) {
-        // level 1: coarse tensor-core pass unproven -> exact fp32 scan for those queries
-        if (path == 2) {
-            for (int j = 0; j < nq; ++j) {
-                if (!(flags[j] & 1)) continue;
-                ix->stats.fallback_gemv += 1;
-                int rc = gemv_pass(ix, q_src, j, 1, k, out, flags);
-                if (rc != ORX_OK) return rc;
-            }
-            CK(cudaStreamSynchronize(st));
-        }
-        // level 2: still unproven (dense near-ties, NaN rows, zero query) -> exhaustive collect
-        for (int j = 0; j < nq; ++j) {
-            if (!(flags[j] & 1)) continue;
-            int cnt = 0;
-            double dk = NAN;
-            if (out_on_dev) {
-                CK(cudaMemcpyAsync(&cnt, out.counts + j, sizeof(int), cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                if (cnt > 0) {
-                    CK(cudaMemcpyAsync(&dk, out.dist + (size_t)j * k + cnt - 1, sizeof(double), cudaMemcpyDeviceToHost, st));
-                    CK(cudaStreamSynchronize(st));
-                }
-            } else {
-                cnt = out.counts[j];
-                if (cnt > 0) dk = out.dist[(size_t)j * k + cnt - 1];
-            }
-            const bool force_all = (flags[j] & 4) != 0 || cnt < k;
-            int rc = exhaustive_query(ix, q_src, j, k, dk, force_all, out);
+        rc = resolve_unproven(ix, q_src, nq, k, out, flags, flags, path, /*host_readable=*/!out_on_dev);
+        if (rc != ORX_OK) return rc;
+    }
+    if (!out_on_dev) {
+        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
+        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
+        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
+    }
+    harvest_scan_events(ix);
+    ix->stats.last_search_ms =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    ix->stats.last_path = path;
+    ix->stats.searches += 1;
+    ix->stats.queries += nq;
+    return ORX_OK;
+}
+
+// =========================================================================== sharded search
+// Layout of one rank's result block for (nq, k): ids | dist | counts | flags (16-byte padded).
+struct SlotLayout {
+    size_t dist_off, counts_off, flags_off, bytes;
+};
+SlotLayout slot_layout(int nq, int k) {
+    SlotLayout L;
+    L.dist_off = (size_t)nq * k * sizeof(orx_id);
+    L.counts_off = L.dist_off + (size_t)nq * k * sizeof(double);
+    L.flags_off = L.counts_off + (size_t)nq * sizeof(int);
+    L.bytes = (L.flags_off + (size_t)nq * sizeof(int) + 15) & ~(size_t)15;
+    return L;
+}
+int sharded_round(orx_index *ix, Exchange *x, int nq, int k, const SearchOut &final_out, const SlotLayout &L,
+                  uint32_t seq) {
+    const int set = seq & 1;
+    char *my_slot = x->base + (size_t)set * x->set_bytes + (size_t)x->rank * x->slot_bytes;
+    orx::launch_publish(my_slot, x->d_peer_slot[set], x->d_peer_flag[set], x->world, L.bytes, seq, ix->stream);
+    const uint32_t *arrival = reinterpret_cast<const uint32_t *>(x->base + x->flags_off + (size_t)set * x->world * XFLAG_STRIDE);
+    orx::launch_merge_wait(x->world, x->rank, nq, k, x->base + (size_t)set * x->set_bytes, x->slot_bytes, L.dist_off,
+                           L.counts_off, L.flags_off, arrival, (int)(XFLAG_STRIDE / 4), seq, final_out.ids,
+                           final_out.dist, final_out.counts, ix->h_flags.p, ix->h_myflags.p, ix->h_redo.p,
+                           ix->stream);
+    ix->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int nq, int k, orx_id *out_ids,
+                          double *out_dist, int *out_counts) {
+    const auto t_begin = std::chrono::steady_clock::now();
+    const bool out_on_dev = is_device_ptr(out_ids);
+    if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
+        return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
+    cudaStream_t st = ix->stream;
+    const size_t nk = (size_t)nq * k;
+    ix->scan_ev_used = 0;
+    const SlotLayout L = slot_layout(nq, k);
+    if (L.bytes > x->slot_bytes) return fail(ORX_ERR_INVALID, "sharded search limited to %d queries per call", XQ_MAX);
+
+    CK(ix->h_flags.ensure(nq));
+    CK(ix->h_myflags.ensure(nq));
+    CK(ix->h_redo.ensure(1));
+    if (!out_on_dev) {
+        CK(ix->h_ids.ensure(nk));
+        CK(ix->h_dist.ensure(nk));
+        CK(ix->h_counts.ensure(nq));
+    }
+    SearchOut final_out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                        out_on_dev ? out_counts : ix->h_counts.p};
+    *ix->h_redo.p = 0;
+
+    const float *q_src = nullptr;
+    int rc = stage_queries(ix, queries, nq, &q_src);
+    if (rc != ORX_OK) return rc;
+
+    // ---- round 1: scan + finalize into my slot, publish to all peers, merge what arrives
+    uint32_t seq = ++x->seq;
+    char *slot = x->base + (size_t)(seq & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;
+    SearchOut mine{reinterpret_cast<orx_id *>(slot), reinterpret_cast<double *>(slot + L.dist_off),
+                   reinterpret_cast<int *>(slot + L.counts_off)};
+    int *slot_flags = reinterpret_cast<int *>(slot + L.flags_off);
+    int path = 1;
+    if (ix->n_live == 0) {
+        // an empty shard contributes nothing (its peers may still hold rows); flags carry the query check
+        CK(cudaMemsetAsync(slot, 0, L.bytes, st));
+        orx::launch_flags_from_prep(ix->prep.p, nq, slot_flags, st);
+        ix->stats.kernel_launches += 1;
+    } else {
+        rc = scan_pass(ix, q_src, nq, k, mine, slot_flags, &path);
+        if (rc != ORX_OK) return rc;
+    }
+    rc = sharded_round(ix, x, nq, k, final_out, L, seq);
+    if (rc != ORX_OK) return rc;
+    CK(cudaStreamSynchronize(st));
+
+    for (int j = 0; j < nq; ++j)
+        if (ix->h_flags.p[j] & 2)
+            return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+    if (*ix->h_redo.p) {
+        // ---- round 2 (every rank sees the same redo word): ranks with unproven queries re-answer them
+        //      exactly, everybody republishes and merges again under the next sequence number.
+        const uint32_t seq2 = ++x->seq;
+        char *slot2 = x->base + (size_t)(seq2 & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;
+        CK(cudaMemcpyAsync(slot2, slot, L.bytes, cudaMemcpyDeviceToDevice, st));
+        SearchOut mine2{reinterpret_cast<orx_id *>(slot2), reinterpret_cast<double *>(slot2 + L.dist_off),
+                        reinterpret_cast<int *>(slot2 + L.counts_off)};
+        int *flags2 = reinterpret_cast<int *>(slot2 + L.flags_off);
+        bool mine_unproven = false;
+        for (int j = 0; j < nq; ++j) mine_unproven |= (ix->h_myflags.p[j] & 1) != 0;
+        if (mine_unproven && ix->n_live > 0) {
+            rc = resolve_unproven(ix, q_src, nq, k, mine2, flags2, ix->h_myflags.p, path, /*host_readable=*/false);
             if (rc != ORX_OK) return rc;
         }
+        *ix->h_redo.p = 0;
+        rc = sharded_round(ix, x, nq, k, final_out, L, seq2);
+        if (rc != ORX_OK) return rc;
         CK(cudaStreamSynchronize(st));
+        if (*ix->h_redo.p) return fail(ORX_ERR_CUDA, "sharded search: a rank could not prove its candidates");
     }
     if (!out_on_dev) {
         memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
@@ -526,6 +686,19 @@ void orx_destroy(orx_index *ix) {
     for (auto &e : ix->ev)
         if (e) cudaEventDestroy(e);
     for (auto &e : ix->scan_ev) cudaEventDestroy(e);
+    if (ix->xchg) {
+        Exchange *x = ix->xchg;
+        for (int r = 0; r < (int)x->peer_base.size(); ++r)
+            if (r != x->rank && x->peer_base[r]) cudaIpcCloseMemHandle(x->peer_base[r]);
+        for (int s = 0; s < 2; ++s) {
+            cudaFree(x->d_peer_slot[s]);
+            cudaFree(x->d_peer_flag[s]);
+        }
+        cudaFree(x->base);
+        delete x;
+    }
+    ix->h_myflags.release();
+    ix->h_redo.release();
     cudaGetLastError();
     delete ix;
 }
@@ -785,6 +958,99 @@ int orx_merge_topk_strided(orx_index *ix, int n_lists, int nq, int k, const orx_
                            out_counts, ix->stream);
     ix->stats.kernel_launches += 1;
     CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+int orx_shard_export(orx_index *ix, int world, int rank, void *handle_out) {
+    if (!ix || !handle_out) return fail(ORX_ERR_INVALID, "null argument");
+    if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(ORX_ERR_INVALID, "bad world/rank %d/%d", rank, world);
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (ix->xchg) return fail(ORX_ERR_INVALID, "shard exchange already initialised");
+    Exchange *x = new Exchange();
+    x->world = world;
+    x->rank = rank;
+    x->slot_bytes = slot_layout(XQ_MAX, ORX_MAX_K).bytes;
+    x->set_bytes = x->slot_bytes * world;
+    x->flags_off = 2 * x->set_bytes;
+    x->total_bytes = x->flags_off + 2 * (size_t)world * XFLAG_STRIDE;
+    cudaError_t e = cudaMalloc(&x->base, x->total_bytes);
+    if (e == cudaSuccess) e = cudaMemset(x->base, 0, x->total_bytes);
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, x->base);
+    if (e != cudaSuccess) {
+        if (x->base) cudaFree(x->base);
+        delete x;
+        cudaGetLastError();
+        return fail(ORX_ERR_CUDA, "shard exchange buffer: %s", cudaGetErrorString(e));
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == ORX_IPC_HANDLE_BYTES, "IPC handle size");
+    memcpy(handle_out, &h, sizeof h);
+    ix->xchg = x;
+    return ORX_OK;
+}
+
+int orx_shard_connect(orx_index *ix, const void *handles, int n_handles) {
+    if (!ix || !handles) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    Exchange *x = ix->xchg;
+    if (!x) return fail(ORX_ERR_INVALID, "call orx_shard_export first");
+    if (x->connected) return fail(ORX_ERR_INVALID, "shard exchange already connected");
+    if (n_handles != x->world) return fail(ORX_ERR_INVALID, "expected %d handles, got %d", x->world, n_handles);
+    x->peer_base.assign(x->world, nullptr);
+    for (int r = 0; r < x->world; ++r) {
+        if (r == x->rank) {
+            x->peer_base[r] = x->base;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, static_cast<const char *>(handles) + (size_t)r * sizeof h, sizeof h);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ORX_ERR_CUDA, "cannot map rank %d's exchange buffer (NVLink/P2P peer access): %s", r,
+                        cudaGetErrorString(e));
+        }
+        x->peer_base[r] = static_cast<char *>(p);
+    }
+    for (int s = 0; s < 2; ++s) {
+        std::vector<void *> slots(x->world);
+        std::vector<uint32_t *> flags(x->world);
+        for (int r = 0; r < x->world; ++r) {
+            slots[r] = x->peer_base[r] + (size_t)s * x->set_bytes + (size_t)x->rank * x->slot_bytes;
+            flags[r] = reinterpret_cast<uint32_t *>(x->peer_base[r] + x->flags_off +
+                                                    ((size_t)s * x->world + x->rank) * XFLAG_STRIDE);
+        }
+        CK(cudaMalloc(&x->d_peer_slot[s], x->world * sizeof(void *)));
+        CK(cudaMalloc(&x->d_peer_flag[s], x->world * sizeof(uint32_t *)));
+        CK(cudaMemcpy(x->d_peer_slot[s], slots.data(), x->world * sizeof(void *), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(x->d_peer_flag[s], flags.data(), x->world * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+    }
+    x->connected = true;
+    return ORX_OK;
+}
+
+int orx_search_sharded(orx_index *ix, const float *queries, int nq, int dim, int k, orx_id *out_ids,
+                       double *out_dist, int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "different vector dimensions %d and %d", ORX_DIM, dim);
+    if (k < 1 || k > ORX_MAX_K) return fail(ORX_ERR_INVALID, "k must be in [1, %d], got %d", ORX_MAX_K, k);
+    if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
+    if (nq == 0) return ORX_OK;
+    if (!queries || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!ix->xchg || !ix->xchg->connected) return fail(ORX_ERR_INVALID, "shard exchange not connected (orx_shard_export / orx_shard_connect)");
+    const bool q_dev = is_device_ptr(queries), o_dev = is_device_ptr(out_ids);
+    for (int q0 = 0; q0 < nq; q0 += XQ_MAX) {      // every rank chunks identically
+        const int m = std::min(XQ_MAX, nq - q0);
+        (void)q_dev; (void)o_dev;
+        int rc = search_sharded_locked(ix, ix->xchg, queries + (size_t)q0 * ORX_DIM, m, k, out_ids + (size_t)q0 * k,
+                                       out_dist + (size_t)q0 * k, out_counts + q0);
+        if (rc != ORX_OK) return rc;
+    }
     return ORX_OK;
 }
 

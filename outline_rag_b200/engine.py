@@ -214,6 +214,40 @@ class Index:
                                          int(stride_bytes), C.c_void_p(ids_out.data_ptr()),
                                          C.c_void_p(dist_out.data_ptr()), C.c_void_p(counts_out.data_ptr())))
 
+    # -- row-sharded search over NVLink peer memory (collective; see sharded.ShardedIndex)
+    def shard_export(self, world: int, rank: int) -> bytes:
+        buf = C.create_string_buffer(_lib.ORX_IPC_HANDLE_BYTES)
+        check(lib.orx_shard_export(self._h, int(world), int(rank), buf))
+        return buf.raw
+
+    def shard_connect(self, handles: Sequence[bytes]) -> None:
+        blob = b"".join(handles)
+        check(lib.orx_shard_connect(self._h, C.c_char_p(blob), len(handles)))
+
+    def search_sharded(self, queries, k: int = 12, out=None):
+        """COLLECTIVE exact top-k over all ranks' shards (`orx_search_sharded`): same calling
+        convention and result layout as :meth:`search`; `out` = reusable (ids, dist, counts) CUDA
+        tensors for the device path."""
+        if _is_cuda_tensor(queries):
+            q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+            nq, dim = q.shape
+            if out is None:
+                out = (torch.empty((nq, k, 2), dtype=torch.int64, device=q.device),
+                       torch.empty((nq, k), dtype=torch.float64, device=q.device),
+                       torch.empty((nq,), dtype=torch.int32, device=q.device))
+            check(lib.orx_search_sharded(self._h, C.c_void_p(q.data_ptr()), nq, dim, int(k),
+                                         C.c_void_p(out[0].data_ptr()), C.c_void_p(out[1].data_ptr()),
+                                         C.c_void_p(out[2].data_ptr())))
+            return out
+        q = _host_f32(queries, "queries")
+        nq, dim = q.shape
+        ids = np.zeros((nq, max(k, 0), 2), np.uint64)
+        dist = np.full((nq, max(k, 0)), np.nan, np.float64)
+        cnt = np.zeros(nq, np.int32)
+        check(lib.orx_search_sharded(self._h, C.c_void_p(q.ctypes.data), nq, dim, int(k), C.c_void_p(ids.ctypes.data),
+                                     C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
+        return ids, dist, cnt
+
     def merge_topk(self, ids, dist, counts, k: int):
         """Merge ``[n_lists, nq, k]`` shard results (NumPy or CUDA tensors) into the global top-k."""
         if _is_cuda_tensor(ids):

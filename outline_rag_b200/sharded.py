@@ -14,6 +14,7 @@ covered by world_size-2 ``gloo`` tests on CPU (tests/test_sharded_gloo.py).
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import numpy as np
@@ -70,6 +71,32 @@ class ShardedIndex:
         self._merge = merge_fn if merge_fn is not None else self.local.merge_topk
         self.gather_launches = 0
         self._plans = {}
+        self._outs = {}
+        # Exchange: "p2p" = the library's fused publish + merge over NVLink peer memory (default on
+        # GPUs); "nccl" = all_gather + orx_merge_topk_strided (baseline, ORX_SHARD_EXCHANGE=nccl).
+        self.exchange = "none" if self.world == 1 else "nccl"
+        want = os.environ.get("ORX_SHARD_EXCHANGE", "p2p")
+        if (self.world > 1 and want == "p2p" and isinstance(self.local, Index)
+                and dist.get_backend(self.group) == "nccl"):
+            self._connect_p2p()
+
+    def _connect_p2p(self) -> None:
+        dev = torch.device(f"cuda:{self.local.device}")
+        handle = self.local.shard_export(self.world, self.rank)
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=dev)
+        everyone = torch.empty(self.world * len(handle), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        blob = everyone.cpu().numpy().tobytes()
+        n = len(handle)
+        ok = torch.ones(1, dtype=torch.int32, device=dev)
+        try:
+            self.local.shard_connect([blob[i * n:(i + 1) * n] for i in range(self.world)])
+        except Exception as e:        # no peer access between these GPUs: every rank falls back together
+            ok.zero_()
+            self._p2p_error = str(e)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            self.exchange = "p2p"
 
     def _plan(self, nq: int, k: int, device):
         """Reusable device buffers for one (nq, k): my result block (the scan's output arrays are
@@ -131,6 +158,17 @@ class ShardedIndex:
         """Global top-k on every rank.  ``queries`` is identical on all ranks (CUDA tensor for the
         NCCL path; NumPy for the CPU/gloo test path).  On the CUDA path the returned tensors are
         reusable per-(nq, k) buffers: they are overwritten by the next search of the same shape."""
+        if self.exchange == "p2p":
+            if isinstance(queries, torch.Tensor) and queries.is_cuda:
+                q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+                key = (q.shape[0], k)
+                out = self._outs.get(key)
+                if out is None:
+                    out = self._outs[key] = (torch.empty((q.shape[0], k, 2), dtype=torch.int64, device=q.device),
+                                             torch.empty((q.shape[0], k), dtype=torch.float64, device=q.device),
+                                             torch.empty((q.shape[0],), dtype=torch.int32, device=q.device))
+                return self.local.search_sharded(q, k, out)
+            return self.local.search_sharded(queries, k)
         if self.world > 1 and isinstance(queries, torch.Tensor) and queries.is_cuda and hasattr(self.local, "search_into"):
             q = queries if queries.dim() == 2 else queries.unsqueeze(0)
             nq = q.shape[0]
