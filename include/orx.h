@@ -137,6 +137,14 @@ int orx_search_sharded(orx_index *idx, const float *queries, int nq, int dim, in
  * out_vecs [n, dim] host; out_found [n] host (1/0). */
 int orx_fetch(orx_index *idx, const orx_id *ids, uint64_t n, float *out_vecs, int *out_found);
 
+/* Snapshot / cold start (the device table is a cache of
+ * `langchain_pg_embedding.embedding`, reference app/database.py:118-131).
+ * orx_export_rows copies live rows [row_start, row_start+n) VERBATIM in the table dtype (fp32: 4096 B,
+ * bf16: 2048 B per row) with their ids to host buffers; orx_import_rows appends such rows (ids must be
+ * new) without re-normalising, so a bf16 table round-trips bit for bit.  rows_raw may be host or device. */
+int orx_export_rows(orx_index *idx, uint64_t row_start, uint64_t n, orx_id *ids_out, void *rows_out);
+int orx_import_rows(orx_index *idx, const orx_id *ids, const void *rows_raw, uint64_t n);
+
 /* Synthetic bge-m3-shaped table generator, bit-identical to
  * outline_rag_b200/synth.py.  Fills dst_device [n_rows, 1024] fp32 with rows
  * row_start .. row_start+n_rows-1.  centres/mean are built on first use. */

@@ -80,6 +80,8 @@ SIGNATURES = {
     "orx_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "orx_merge_topk": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "orx_merge_topk_strided": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_uint64, _vp, _vp, _vp]),
+    "orx_export_rows": (C.c_int, [_vp, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "orx_import_rows": (C.c_int, [_vp, _vp, _vp, C.c_uint64]),
     "orx_shard_export": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "orx_shard_connect": (C.c_int, [_vp, _vp, C.c_int]),
     "orx_search_sharded": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),

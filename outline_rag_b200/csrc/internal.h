@@ -67,6 +67,8 @@ void launch_validate_rows(const float *src, uint64_t n, int *flag, cudaStream_t 
 void launch_commit_rows(int dtype, const float *src, const uint32_t *src_idx, const uint32_t *dst_row,
                         const orx_id *ids, uint32_t n, void *table, float *scale, double *n2,
                         orx_id *row_ids, cudaStream_t st);
+void launch_adopt_rows(int dtype, const void *table, uint32_t row0, uint32_t n, const orx_id *ids, float *scale,
+                       double *n2, orx_id *row_ids, int *flag, cudaStream_t st);
 void launch_move_rows(int dtype, const uint32_t *src_row, const uint32_t *dst_row, uint32_t n,
                       void *table, float *scale, double *n2, orx_id *row_ids, cudaStream_t st);
 void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint32_t n, float *out,

@@ -961,6 +961,65 @@ int orx_merge_topk_strided(orx_index *ix, int n_lists, int nq, int k, const orx_
     return ORX_OK;
 }
 
+int orx_export_rows(orx_index *ix, uint64_t row_start, uint64_t n, orx_id *ids_out, void *rows_out) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n == 0) return ORX_OK;
+    if (!ids_out || !rows_out) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (row_start + n > ix->n_live) return fail(ORX_ERR_INVALID, "rows [%llu, %llu) exceed the %llu live rows",
+                                                (unsigned long long)row_start, (unsigned long long)(row_start + n),
+                                                (unsigned long long)ix->n_live);
+    const size_t rb = ORX_DIM * elem_size(ix->dtype);
+    memcpy(ids_out, ix->host_row_ids.data() + row_start, n * sizeof(orx_id));
+    CK(cudaMemcpyAsync(rows_out, static_cast<const char *>(ix->table) + row_start * rb, n * rb, cudaMemcpyDeviceToHost,
+                       ix->stream));
+    CK(cudaStreamSynchronize(ix->stream));
+    return ORX_OK;
+}
+
+int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint64_t n) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n == 0) return ORX_OK;
+    if (!ids || !rows_raw) return fail(ORX_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    {   // every id must be new: this is an append, not an upsert
+        std::unordered_map<orx_id, int, IdHash, IdEq> seen;
+        seen.reserve(n);
+        for (uint64_t i = 0; i < n; ++i)
+            if (ix->map.find(ids[i]) != ix->map.end() || !seen.emplace(ids[i], 1).second)
+                return fail(ORX_ERR_INVALID, "orx_import_rows: id %llu of the batch is already present", (unsigned long long)i);
+    }
+    int rc = grow_table(ix, ix->n_live + n);
+    if (rc != ORX_OK) return rc;
+    const size_t rb = ORX_DIM * elem_size(ix->dtype);
+    const uint64_t row0 = ix->n_live;
+    CK(ix->d_ids.ensure(n));
+    CK(ix->d_flag.ensure(1));
+    CK(ix->h_flag.ensure(1));
+    CK(cudaMemsetAsync(ix->d_flag.p, 0, sizeof(int), st));
+    // straight into the table tail: invisible to searches until n_live moves
+    CK(cudaMemcpyAsync(static_cast<char *>(ix->table) + row0 * rb, rows_raw, n * rb,
+                       is_device_ptr(rows_raw) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ix->d_ids.p, ids, n * sizeof(orx_id), cudaMemcpyHostToDevice, st));
+    orx::launch_adopt_rows(ix->dtype, ix->table, (uint32_t)row0, (uint32_t)n, ix->d_ids.p, ix->scale, ix->n2,
+                           ix->row_ids, ix->d_flag.p, st);
+    ix->stats.kernel_launches += 1;
+    CK(cudaMemcpyAsync(ix->h_flag.p, ix->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
+    ix->host_row_ids.resize(row0 + n);
+    for (uint64_t i = 0; i < n; ++i) {
+        ix->host_row_ids[row0 + i] = ids[i];
+        ix->map.emplace(ids[i], (uint32_t)(row0 + i));
+    }
+    ix->n_live = row0 + n;
+    return ORX_OK;
+}
+
 int orx_shard_export(orx_index *ix, int world, int rank, void *handle_out) {
     if (!ix || !handle_out) return fail(ORX_ERR_INVALID, "null argument");
     if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(ORX_ERR_INVALID, "bad world/rank %d/%d", rank, world);

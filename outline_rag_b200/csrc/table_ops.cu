@@ -98,6 +98,52 @@ void launch_commit_rows(int dtype, const float *src, const uint32_t *src_idx, co
             src, src_idx, dst_row, ids, n, static_cast<__nv_bfloat16 *>(table), scale, n2, row_ids);
 }
 
+// Bulk load (snapshot restore / cold start): the rows were copied VERBATIM (table dtype) to the
+// table tail [row0, row0+n); this computes what upsert would have: finite check, canonical |x|^2 of
+// the row as stored, 1/|x|, the id column.  Nothing is visible to searches until the host bumps
+// the live row count, so a NaN/Inf batch is rejected without side effects.
+template <typename T>
+__global__ void __launch_bounds__(256)
+adopt_rows_kernel(const T *__restrict__ table, uint32_t row0, uint32_t n, const orx_id *__restrict__ ids,
+                  float *__restrict__ scale, double *__restrict__ n2_out, orx_id *__restrict__ row_ids,
+                  int *__restrict__ flag) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const uint32_t n_gw = gridDim.x * (blockDim.x >> 5);
+    for (uint32_t i = gw; i < n; i += n_gw) {
+        const uint32_t r = row0 + i;
+        const T *row = table + (size_t)r * ORX_DIM;
+        double p[32];
+        bool bad = false;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float v = row_elem<T>(row, lane + 32 * j);
+            bad |= !isfinite(v);
+            p[j] = __dmul_rn((double)v, (double)v);
+        }
+        const double n2 = bcast_lane0(canon_tree_1024(p));
+        if (__any_sync(FULL_MASK, bad) && lane == 0) atomicOr(flag, 1);
+        if (lane == 0) {
+            scale[r] = scale_from_n2(n2);
+            n2_out[r] = n2;
+            row_ids[r] = ids[i];
+        }
+    }
+}
+
+void launch_adopt_rows(int dtype, const void *table, uint32_t row0, uint32_t n, const orx_id *ids, float *scale,
+                       double *n2, orx_id *row_ids, int *flag, cudaStream_t st) {
+    if (n == 0) return;
+    uint32_t blocks = (n + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (dtype == ORX_DTYPE_F32)
+        adopt_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(table), row0, n, ids, scale, n2,
+                                                         row_ids, flag);
+    else
+        adopt_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16 *>(table), row0, n,
+                                                                 ids, scale, n2, row_ids, flag);
+}
+
 // one warp per relocated row; sources (>= new live count) and destinations (< new live count)
 // are disjoint sets, so all moves run in parallel.
 __global__ void __launch_bounds__(256)

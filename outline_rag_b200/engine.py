@@ -214,6 +214,55 @@ class Index:
                                          int(stride_bytes), C.c_void_p(ids_out.data_ptr()),
                                          C.c_void_p(dist_out.data_ptr()), C.c_void_p(counts_out.data_ptr())))
 
+    # -- snapshot / cold start
+    SNAPSHOT_CHUNK = 65536
+
+    def save(self, path: str) -> dict:
+        """Write `manifest.json`, `ids.bin` (uint64 [n,2]) and `vecs.bin` (rows verbatim in the table
+        dtype) under `path`.  Postgres stays the source of truth; this avoids re-loading 41 GB of
+        vectors through SQL text on restart."""
+        import json
+        import os
+        os.makedirs(path, exist_ok=True)
+        n = len(self)
+        rb = ORX_DIM * (4 if self.dtype == "fp32" else 2)
+        manifest = {"format": "orx-snapshot-1", "dtype": self.dtype, "dim": ORX_DIM, "rows": n, "row_bytes": rb}
+        ids = np.lib.format.open_memmap(os.path.join(path, "ids.npy"), mode="w+", dtype=np.uint64, shape=(n, 2))
+        vecs = np.lib.format.open_memmap(os.path.join(path, "vecs.npy"), mode="w+", dtype=np.uint8, shape=(n, rb))
+        for s in range(0, n, self.SNAPSHOT_CHUNK):
+            m = min(self.SNAPSHOT_CHUNK, n - s)
+            ci = np.empty((m, 2), np.uint64)
+            cv = np.empty((m, rb), np.uint8)
+            check(lib.orx_export_rows(self._h, s, m, C.c_void_p(ci.ctypes.data), C.c_void_p(cv.ctypes.data)))
+            ids[s:s + m] = ci
+            vecs[s:s + m] = cv
+        ids.flush()
+        vecs.flush()
+        with open(os.path.join(path, "manifest.json"), "w") as f:
+            json.dump(manifest, f)
+        return manifest
+
+    @classmethod
+    def load(cls, path: str, device: int | None = None, capacity: int = 0) -> "Index":
+        import json
+        import os
+        with open(os.path.join(path, "manifest.json")) as f:
+            man = json.load(f)
+        if man.get("format") != "orx-snapshot-1" or man["dim"] != ORX_DIM:
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, f"not an orx snapshot: {path}")
+        n = int(man["rows"])
+        ix = cls(man["dtype"], max(capacity, n), device)
+        ids = np.load(os.path.join(path, "ids.npy"), mmap_mode="r")
+        vecs = np.load(os.path.join(path, "vecs.npy"), mmap_mode="r")
+        if ids.shape != (n, 2) or vecs.shape != (n, man["row_bytes"]):
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "snapshot files do not match the manifest")
+        for s in range(0, n, cls.SNAPSHOT_CHUNK):
+            m = min(cls.SNAPSHOT_CHUNK, n - s)
+            ci = np.ascontiguousarray(ids[s:s + m])
+            cv = np.ascontiguousarray(vecs[s:s + m])
+            check(lib.orx_import_rows(ix._h, C.c_void_p(ci.ctypes.data), C.c_void_p(cv.ctypes.data), m))
+        return ix
+
     # -- row-sharded search over NVLink peer memory (collective; see sharded.ShardedIndex)
     def shard_export(self, world: int, rank: int) -> bytes:
         buf = C.create_string_buffer(_lib.ORX_IPC_HANDLE_BYTES)

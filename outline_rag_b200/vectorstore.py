@@ -26,6 +26,7 @@ from typing import Any, Iterable, Optional, Sequence
 
 import numpy as np
 
+from .batcher import QueryBatcher
 from .engine import Index, ids_to_array, ids_to_uuid_strs
 
 try:  # use the real class when the host application has langchain installed
@@ -89,8 +90,11 @@ class GpuRetriever:
 
 class GpuVectorStore:
     def __init__(self, index: Index, embedding_service, doc_store=None,
-                 metadata_columns: Optional[list[str]] = None, table_name: str = "langchain_pg_embedding"):
+                 metadata_columns: Optional[list[str]] = None, table_name: str = "langchain_pg_embedding",
+                 batch_window_ms: Optional[float] = None, max_batch: int = 256):
         self.index = index
+        # micro-batching of concurrent by-vector searches; None = one scan per request
+        self.batcher = QueryBatcher(index, max_batch, batch_window_ms) if batch_window_ms is not None else None
         self.embedding_service = embedding_service
         self.doc_store = doc_store if doc_store is not None else MemoryDocStore()
         self.metadata_columns = list(metadata_columns or DEFAULT_METADATA_COLUMNS)
@@ -100,7 +104,8 @@ class GpuVectorStore:
     @classmethod
     async def create(cls, engine=None, embedding_service=None, table_name: str = "langchain_pg_embedding",
                      metadata_columns: Optional[list[str]] = None, *, dtype: str = "fp32", capacity: int = 0,
-                     device: Optional[int] = None, doc_store=None, **_: Any) -> "GpuVectorStore":
+                     device: Optional[int] = None, doc_store=None, batch_window_ms: Optional[float] = None,
+                     max_batch: int = 256, **_: Any) -> "GpuVectorStore":
         """Same call shape as ``AsyncPGVectorStore.create`` (reference app/rag.py:69-79).
         ``engine`` (the PGEngine) is accepted and handed to the doc store factory if it is
         callable; the vector column itself now lives in HBM."""
@@ -109,7 +114,7 @@ class GpuVectorStore:
         if callable(doc_store):
             doc_store = doc_store(engine)
         index = await asyncio.to_thread(Index, dtype, capacity, device)
-        return cls(index, embedding_service, doc_store, metadata_columns, table_name)
+        return cls(index, embedding_service, doc_store, metadata_columns, table_name, batch_window_ms, max_batch)
 
     @classmethod
     def create_sync(cls, embedding_service, **kw) -> "GpuVectorStore":
@@ -195,6 +200,9 @@ class GpuVectorStore:
         return [self._hydrate(ids[i], dist[i], int(cnt[i])) for i in range(ids.shape[0])]
 
     async def asimilarity_search_with_score_by_vector(self, embedding, k: int = 4, filter=None, **kw: Any):
+        if self.batcher is not None and filter is None:
+            ids, dist = await self.batcher.search(embedding, k)      # coalesced with concurrent requests
+            return await asyncio.to_thread(self._hydrate, ids, dist, len(dist))
         return await asyncio.to_thread(self.similarity_search_with_score_by_vector, embedding, k, filter)
 
     async def asimilarity_search_by_vector(self, embedding, k: int = 4, **kw: Any):

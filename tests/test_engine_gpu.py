@@ -448,3 +448,37 @@ def test_gathered_block_merge_equals_single_table(Index, small_table):
     for i in range(nq):
         w_ids, w_d = O.topk_exact(X[:n], ids, Q[i], K)
         assert np.array_equal(m_ids[i], w_ids) and np.array_equal(m_d[i].view(np.uint64), w_d.view(np.uint64))
+
+
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_snapshot_roundtrip_is_bit_identical(Index, small_table, tmp_path, dtype):
+    """save -> load reproduces the table verbatim (bf16 rows are NOT re-normalised), so searches and
+    fetches are bit-identical; a snapshot with a NaN row is rejected without side effects."""
+    import outline_rag_b200 as orx
+    X, Q, _ = small_table
+    n = 5000
+    ids = _ids(n, 7)
+    with Index(dtype) as a:
+        a.upsert(ids, X[:n])
+        a.delete(ids[10:30])                                    # compaction reorders rows: the snapshot keeps that order
+        man = a.save(str(tmp_path / "snap"))
+        assert man["rows"] == n - 20 and man["dtype"] == dtype
+        ra = a.search(Q[:6], K)
+        fa, _ = a.fetch(ids[:64])
+    b = orx.Index.load(str(tmp_path / "snap"))
+    try:
+        assert len(b) == n - 20 and b.dtype == dtype
+        rb = b.search(Q[:6], K)
+        fb, found = b.fetch(ids[:64])
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1].view(np.uint64), rb[1].view(np.uint64))
+        assert np.array_equal(fa.view(np.uint32), fb.view(np.uint32)) and found[:10].all() and not found[10:30].any()
+        b.upsert(ids[10:12], X[10:12])                          # the restored table keeps working
+        assert len(b) == n - 18
+    finally:
+        b.close()
+    # corrupt the snapshot with a NaN: load must fail
+    v = np.load(tmp_path / "snap" / "vecs.npy", mmap_mode="r+")
+    v[3, 0:4 if dtype == "fp32" else 2] = 0xFF
+    v.flush()
+    with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
+        orx.Index.load(str(tmp_path / "snap"))
