@@ -344,9 +344,16 @@ constexpr int ZERO_COPY_MAX_Q = 16;     // query batches up to this size are rea
 // ---- query staging: *q_src is what the rescoring kernels read (device memory); launches prep
 int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_src) {
     cudaStream_t st = ix->stream;
-    CK(ix->qhat.ensure((size_t)nq * ORX_DIM));
-    CK(ix->qhat16.ensure((size_t)nq * ORX_DIM));
+    // the tcgen05 scan reads query tiles of 128 rows: keep the buffers padded (and the pad zeroed) so
+    // its TMA never touches an out-of-range row (measured: mostly-out-of-range query boxes cost ~40 %)
+    const size_t nq_pad = ((size_t)nq + 127) / 128 * 128;
+    CK(ix->qhat.ensure(nq_pad * ORX_DIM));
+    CK(ix->qhat16.ensure(nq_pad * ORX_DIM));
     CK(ix->prep.ensure(nq));
+    if (nq_pad != (size_t)nq && nq > 1) {
+        CK(cudaMemsetAsync(ix->qhat.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(float), st));
+        CK(cudaMemsetAsync(ix->qhat16.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(__nv_bfloat16), st));
+    }
     if (is_device_ptr(queries)) {
         *q_src = queries;
         orx::launch_prep_queries(queries, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);

@@ -506,7 +506,8 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
         CUtensorMap map_q, map_x;
         const void *qbase = tf32 ? (const void *)(qhat + (size_t)q0 * ORX_DIM) : (const void *)(qhat16 + (size_t)q0 * ORX_DIM);
-        if (!encode_map(&map_q, qbase, (uint64_t)m, tf32, TILE_M)) return ORX_ERR_CUDA;
+        // qhat / qhat16 are padded with zero rows to a multiple of TILE_M by the caller (stage_queries)
+        if (!encode_map(&map_q, qbase, (uint64_t)m_tiles * TILE_M, tf32, TILE_M)) return ORX_ERR_CUDA;
         if (!encode_map(&map_x, table, (uint64_t)n_rows, tf32, TILE_N)) return ORX_ERR_CUDA;
         cudaMemsetAsync(p->gthr, 0, (size_t)m * sizeof(uint32_t), st);
         if (ev_begin && q0 == 0) cudaEventRecord(ev_begin, st);
