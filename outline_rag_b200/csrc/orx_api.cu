@@ -344,9 +344,9 @@ constexpr int ZERO_COPY_MAX_Q = 16;     // query batches up to this size are rea
 // ---- query staging: *q_src is what the rescoring kernels read (device memory); launches prep
 int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_src) {
     cudaStream_t st = ix->stream;
-    // the tcgen05 scan reads query tiles of 128 rows: keep the buffers padded (and the pad zeroed) so
+    // the tcgen05 scan reads query tiles of 128 rows (256 per CTA pair): keep the buffers padded (and the pad zeroed) so
     // its TMA never touches an out-of-range row (measured: mostly-out-of-range query boxes cost ~40 %)
-    const size_t nq_pad = ((size_t)nq + 127) / 128 * 128;
+    const size_t nq_pad = ((size_t)nq + 255) / 256 * 256;
     CK(ix->qhat.ensure(nq_pad * ORX_DIM));
     CK(ix->qhat16.ensure(nq_pad * ORX_DIM));
     CK(ix->prep.ensure(nq));

@@ -27,6 +27,7 @@
 // Algorithmic work per launch: bytes = rows*1024*sizeof(elem); flops = 2*rows*1024*queries.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <string>
 
@@ -48,6 +49,13 @@ constexpr int CAND = 64;               // candidate slots per (query, CTA) = fin
 constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;
 constexpr int SMEM_SCALE = 2 * TILE_N * 4;
 constexpr int SMEM_TOTAL = SMEM_MAIN + SMEM_SCALE + 256 + 1024;   // + barriers + alignment slack
+
+// CTA-pair kernel: each CTA stages its 128 queries + HALF of the 256-row table tile per K chunk
+constexpr int STAGES2 = 6;
+constexpr int B2_BYTES = (TILE_N / 2) * 128;                 // 16 KB
+constexpr int STAGE2_BYTES = A_BYTES + B2_BYTES;             // 32 KB
+constexpr int SMEM2_MAIN = STAGES2 * STAGE2_BYTES;
+constexpr int SMEM2_TOTAL = SMEM2_MAIN + SMEM_SCALE + 256 + 1024;
 
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t HINT_EVICT_FIRST = 0x12F0000000000000ull;
@@ -122,6 +130,51 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- CTA-pair (cta_group::2) variants
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `local_addr` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// each CTA of the pair loads into ITS OWN smem; the bytes are counted on the LEADER's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0,
+                                                 int c1, uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1), "l"(hint) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {      // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+        ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void tc_mma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if constexpr (TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
 // K-major, 128-byte swizzle shared-memory matrix descriptor (sm_100 "version 1"):
 // start>>4 | LBO(=1, unused for swizzled K-major)<<16 | SBO(= 8 rows x 128 B = 1024 B)>>4 <<32 | layout SWIZZLE_128B.
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
@@ -134,9 +187,9 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 // instruction descriptor: D fp32, A/B bf16 (1) or tf32 (2), both K-major, N>>3 at [17,23), M>>4 at [24,29)
-__host__ __device__ constexpr uint32_t make_idesc(bool tf32) {
+__host__ __device__ constexpr uint32_t make_idesc(bool tf32, int m = TILE_M) {
     return (1u << 4) | ((tf32 ? 2u : 1u) << 7) | ((tf32 ? 2u : 1u) << 10) | ((uint32_t)(TILE_N >> 3) << 17) |
-           ((uint32_t)(TILE_M >> 4) << 24);
+           ((uint32_t)(m >> 4) << 24);
 }
 
 // ------------------------------------------------------------------ candidate list upkeep
@@ -179,12 +232,139 @@ __device__ __forceinline__ void coop_compact(uint64_t *list, int L, int lane, in
     }
 }
 
+// ------------------------------------------------------------------------------- epilogue
+// Shared by the 1-CTA and the 2-CTA kernels: 4 warps, thread = one query (TMEM lane), see the file
+// header.  `arrive_empty(buf)` hands accumulator buffer `buf` back to the MMA issuer.
+template <class ArriveEmpty>
+__device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int n_slots, uint32_t n_tiles,
+                                              const float *__restrict__ scale, uint32_t n_rows, int k, float margin,
+                                              uint64_t *__restrict__ partial, float *__restrict__ floor_out,
+                                              uint32_t *__restrict__ gthr_all, float *s_scale, uint32_t bar_tfull,
+                                              uint32_t tmem_base, int ew, int lane, ArriveEmpty arrive_empty,
+                                              int dbg = 0) {
+    const int et = ew * 32 + lane;                          // 0..127
+    const int q = q_base + ew * 32 + lane;
+    const bool active = q < nq;
+    uint64_t *buf_keys = partial + ((size_t)(active ? q : 0) * n_slots + slot) * CAND;
+    uint32_t *gthr = gthr_all + (active ? q : 0);
+    float thr = __int_as_float(0xff800000);                 // -inf
+    int cnt = 0;
+    bool overflow = false;
+    uint32_t buf = 0, tphase = 0;
+    // 1/|x| of the NEXT tile is fetched while the current one is scanned (the loads miss to HBM)
+    float sc_next[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const uint32_t r = (uint32_t)slot * TILE_N + et + 128 * h;
+        sc_next[h] = ((uint32_t)slot < n_tiles && r < n_rows) ? __ldg(scale + r) : __int_as_float(0x7fc00000);
+    }
+    for (uint32_t t = slot; t < n_tiles; t += n_slots) {
+        const uint32_t n0 = t * TILE_N;
+        // stage this tile's 1/|x| (NaN beyond the table end: never a candidate)
+        float *sc = s_scale + buf * TILE_N;
+        bool special = false;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float s = sc_next[h];
+            special |= !(fabsf(s) < __int_as_float(0x7f800000));      // inf or NaN
+            sc[et + 128 * h] = s;
+            const uint32_t rn = n0 + (uint32_t)n_slots * TILE_N + et + 128 * h;
+            sc_next[h] = (t + n_slots < n_tiles && rn < n_rows) ? __ldg(scale + rn) : __int_as_float(0x7fc00000);
+        }
+        uint32_t tile_special;
+        asm volatile(
+            "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\t"
+            "bar.red.or.pred p, 1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(tile_special) : "r"((uint32_t)special) : "memory");
+        if (active) {
+            const uint32_t g = *reinterpret_cast<volatile uint32_t *>(gthr);
+            if (g) thr = fmaxf(thr, ord_to_float(g));
+        }
+        mbar_wait(bar_tfull + 8 * buf, tphase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * TILE_N;
+#pragma unroll 1
+        for (int c = 0; c < ((dbg & 1) ? 0 : TILE_N / 32); ++c) {      // dbg bit 0: timing experiment, no column scan
+            uint32_t v[32];
+            tmem_ld32(taddr + c * 32, v);
+            tmem_ld_wait();
+            const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c * 32);
+            float s[32];
+            float mx = __int_as_float(0xff800000);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 f = sc4[j4];
+                s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * f.x;
+                s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
+                s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
+                s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
+                mx = fmaxf(fmaxf(mx, fmaxf(s[4 * j4 + 0], s[4 * j4 + 1])), fmaxf(s[4 * j4 + 2], s[4 * j4 + 3]));
+            }
+            // fmaxf ignores NaN (zero-norm rows, rows beyond the end); irregular rows need the slow path
+            const bool hit = active && ((mx > thr) || tile_special);
+            if (!__any_sync(FULL_MASK, hit)) continue;
+            // ---- slow path (warp-uniform): some lane has survivors in these 32 columns
+            uint32_t always = 0;
+            if (tile_special) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float sj = sc[c * 32 + j];
+                    if (sj == __int_as_float(0x7f800000)) always |= 1u << j;      // irregular magnitude
+                    else if (sj != sj) s[j] = __int_as_float(0xff800000);         // zero-norm / beyond the end
+                }
+            }
+            uint32_t mask = 0;
+            for (int round = 0;; ++round) {
+                mask = 0;
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) mask |= (s[j] > thr) ? (1u << j) : 0u;
+                    mask = (mask & ~always) | (overflow ? 0u : always);
+                }
+                const unsigned need = __ballot_sync(FULL_MASK, active && cnt + __popc(mask) > CAND);
+                if (!need) break;
+                if (round == 1) {
+                    // near-ties wider than the list: the query is re-answered by the fp32 scan
+                    if (need & (1u << lane)) {
+                        overflow = true;
+                        thr = __int_as_float(0x7f800000);
+                        atomicMax(gthr, float_to_ord(thr));
+                    }
+                    continue;
+                }
+                unsigned todo = need;
+                while (todo) {
+                    const int L = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    uint64_t *list_L = partial + ((size_t)(q - lane + L) * n_slots + slot) * CAND;
+                    coop_compact(list_L, L, lane, cnt, thr, k, margin, gthr_all + (q - lane + L));
+                }
+            }
+            if (mask) {
+                const uint32_t row0 = n0 + c * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (mask & (1u << j))
+                        buf_keys[cnt++] = make_key((always >> j) & 1u ? ORD_ALWAYS : float_to_ord(s[j]), row0 + j);
+            }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_empty(buf);
+        if (++buf == 2) { buf = 0; tphase ^= 1; }
+    }
+    if (active) {
+        for (int i = cnt; i < CAND; ++i) buf_keys[i] = 0ull;
+        floor_out[(size_t)q * n_slots + slot] = overflow ? __int_as_float(0x7f800000) : thr;
+    }
+}
+
 template <bool TF32>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const float *__restrict__ scale, uint32_t n_rows, int nq, int m_tiles, int n_slots, int k,
                  float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
-                 uint32_t *__restrict__ gthr_all) {
+                 uint32_t *__restrict__ gthr_all, int dbg) {
     constexpr int ES = TF32 ? 4 : 2;                // operand element size
     constexpr int BLOCK_K = 128 / ES;               // elements per 128-byte swizzle row
     constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;     // 16 (bf16) / 32 (tf32)
@@ -239,9 +419,12 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int kc = 0; kc < K_CHUNKS; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    mbar_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-                    tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * BLOCK_K, m_tile * TILE_M, HINT_EVICT_LAST);
-                    tma_load_2d(sa + A_BYTES, &map_x, bar_full + 8 * stage, kc * BLOCK_K, (int)(t * TILE_N), hint_x);
+                    // dbg bits 1 / 2 (timing experiments only): do not load the query / table operand
+                    mbar_expect_tx(bar_full + 8 * stage, ((dbg & 2) ? 0 : A_BYTES) + ((dbg & 4) ? 0 : B_BYTES));
+                    if (!(dbg & 2))
+                        tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * BLOCK_K, m_tile * TILE_M, HINT_EVICT_LAST);
+                    if (!(dbg & 4))
+                        tma_load_2d(sa + A_BYTES, &map_x, bar_full + 8 * stage, kc * BLOCK_K, (int)(t * TILE_N), hint_x);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -272,114 +455,9 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
     } else if (warp >= 4) {
         // ========================================================================= epilogue
-        const int ew = warp - 4;                                // == warp % 4: TMEM lane quarter
-        const int et = threadIdx.x - 128;                       // 0..127
-        const int q = m_tile * TILE_M + ew * 32 + lane;
-        const bool active = q < nq;
-        uint64_t *buf_keys = partial + ((size_t)(active ? q : 0) * n_slots + slot) * CAND;
-        uint32_t *gthr = gthr_all + (active ? q : 0);
-        float thr = __int_as_float(0xff800000);                 // -inf
-        int cnt = 0;
-        bool overflow = false;
-        uint32_t buf = 0, tphase = 0;
-        for (uint32_t t = slot; t < n_tiles; t += n_slots) {
-            const uint32_t n0 = t * TILE_N;
-            // stage this tile's 1/|x| (NaN beyond the table end: never a candidate)
-            float *sc = s_scale + buf * TILE_N;
-            bool special = false;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const uint32_t r = n0 + et + 128 * h;
-                const float s = r < n_rows ? __ldg(scale + r) : __int_as_float(0x7fc00000);
-                special |= !(fabsf(s) < __int_as_float(0x7f800000));      // inf or NaN
-                sc[et + 128 * h] = s;
-            }
-            uint32_t tile_special;
-            asm volatile(
-                "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\t"
-                "bar.red.or.pred p, 1, 128, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                : "=r"(tile_special) : "r"((uint32_t)special) : "memory");
-            if (active) {
-                const uint32_t g = *reinterpret_cast<volatile uint32_t *>(gthr);
-                if (g) thr = fmaxf(thr, ord_to_float(g));
-            }
-            mbar_wait(bar_tfull + 8 * buf, tphase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * TILE_N;
-#pragma unroll 1
-            for (int c = 0; c < TILE_N / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(taddr + c * 32, v);
-                tmem_ld_wait();
-                const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c * 32);
-                float s[32];
-                float mx = __int_as_float(0xff800000);
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 f = sc4[j4];
-                    s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * f.x;
-                    s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
-                    s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
-                    s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
-                    mx = fmaxf(fmaxf(mx, fmaxf(s[4 * j4 + 0], s[4 * j4 + 1])), fmaxf(s[4 * j4 + 2], s[4 * j4 + 3]));
-                }
-                // fmaxf ignores NaN (zero-norm rows, rows beyond the end); irregular rows need the slow path
-                const bool hit = active && ((mx > thr) || tile_special);
-                if (!__any_sync(FULL_MASK, hit)) continue;
-                // ---- slow path (warp-uniform): some lane has survivors in these 32 columns
-                uint32_t always = 0;
-                if (tile_special) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sj = sc[c * 32 + j];
-                        if (sj == __int_as_float(0x7f800000)) always |= 1u << j;      // irregular magnitude
-                        else if (sj != sj) s[j] = __int_as_float(0xff800000);         // zero-norm / beyond the end
-                    }
-                }
-                uint32_t mask = 0;
-                for (int round = 0;; ++round) {
-                    mask = 0;
-                    if (active) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) mask |= (s[j] > thr) ? (1u << j) : 0u;
-                        mask = (mask & ~always) | (overflow ? 0u : always);
-                    }
-                    const unsigned need = __ballot_sync(FULL_MASK, active && cnt + __popc(mask) > CAND);
-                    if (!need) break;
-                    if (round == 1) {
-                        // near-ties wider than the list: the query is re-answered by the fp32 scan
-                        if (need & (1u << lane)) {
-                            overflow = true;
-                            thr = __int_as_float(0x7f800000);
-                            atomicMax(gthr, float_to_ord(thr));
-                        }
-                        continue;
-                    }
-                    unsigned todo = need;
-                    while (todo) {
-                        const int L = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        uint64_t *list_L = partial + ((size_t)(q - lane + L) * n_slots + slot) * CAND;
-                        coop_compact(list_L, L, lane, cnt, thr, k, margin, gthr_all + (q - lane + L));
-                    }
-                }
-                if (mask) {
-                    const uint32_t row0 = n0 + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        if (mask & (1u << j))
-                            buf_keys[cnt++] = make_key((always >> j) & 1u ? ORD_ALWAYS : float_to_ord(s[j]), row0 + j);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * buf);
-            if (++buf == 2) { buf = 0; tphase ^= 1; }
-        }
-        if (active) {
-            for (int i = cnt; i < CAND; ++i) buf_keys[i] = 0ull;
-            floor_out[(size_t)q * n_slots + slot] = overflow ? __int_as_float(0x7f800000) : thr;
-        }
+        epilogue_loop(m_tile * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin, partial, floor_out,
+                      gthr_all, s_scale, bar_tfull, tmem_base, warp - 4, lane,
+                      [&](uint32_t b) { mbar_arrive(bar_tempty + 8 * b); }, dbg);
     }
 
     tc_fence_before();
@@ -387,6 +465,130 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ CTA-pair kernel (cta_group::2)
+// For batches of more than 128 queries.  A cluster of two CTAs (one TPC) computes
+//     D[256 queries x 256 rows] : UMMA M=256, each CTA holds its 128 queries (A) and HALF of the
+// table tile (B, 128 rows); the hardware shares the B halves, so per CTA and K chunk only 32 KB are
+// staged instead of 48 KB.  That halves the L2->smem traffic of the table operand and buys a 6-stage
+// ring (3072 MMA cycles of prefetch instead of 2048).  Only the leader CTA issues MMAs; commits are
+// multicast to both CTAs' barriers; both CTAs' TMA bytes are counted on the leader's full barrier;
+// both CTAs' epilogues hand accumulators back by arriving on the leader's tmem-empty barrier.
+template <bool TF32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
+scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
+                  const float *__restrict__ scale, uint32_t n_rows, int nq, int m_pairs, int n_slots, int k,
+                  float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
+                  uint32_t *__restrict__ gthr_all, int dbg) {
+    constexpr int ES = TF32 ? 4 : 2;
+    constexpr int BLOCK_K = 128 / ES;
+    constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;
+    constexpr uint32_t IDESC = make_idesc(TF32, 2 * TILE_M);
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float *s_scale = reinterpret_cast<float *>(smem + SMEM2_MAIN);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + SMEM2_MAIN + SMEM_SCALE);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bars + 20);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(bars);              // [STAGES2]   (the leader's are used)
+    const uint32_t bar_empty = bar_full + 8 * STAGES2;     // [STAGES2]   per CTA
+    const uint32_t bar_tfull = bar_empty + 8 * STAGES2;    // [2]         per CTA
+    const uint32_t bar_tempty = bar_tfull + 16;            // [2]         (the leader's are used)
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = cluster_ctarank();
+    const bool leader = cta_rank == 0;
+    const int pair = blockIdx.x >> 1;
+    const int m_pair = pair % m_pairs;
+    const int slot = pair / m_pairs;
+    const uint32_t n_tiles = (n_rows + TILE_N - 1) / TILE_N;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 8);             // 4 epilogue warps x 2 CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // barriers of BOTH CTAs are initialised
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ============================================== TMA producer (one per CTA, own smem)
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+            const uint64_t hint_x = (m_pairs > 1) ? HINT_EVICT_NORMAL : HINT_EVICT_FIRST;
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = slot; t < n_tiles; t += n_slots) {
+                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                    const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+                    const uint32_t full_leader = map_to_cta(bar_full + 8 * stage, 0);
+                    if (leader)
+                        mbar_expect_tx(bar_full + 8 * stage, 2 * (((dbg & 2) ? 0 : A_BYTES) + ((dbg & 4) ? 0 : B2_BYTES)));
+                    if (!(dbg & 2))
+                        tma_load_2d_pair(sa, &map_q, full_leader, kc * BLOCK_K,
+                                         m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, HINT_EVICT_LAST);
+                    if (!(dbg & 4))
+                        tma_load_2d_pair(sa + A_BYTES, &map_x, full_leader, kc * BLOCK_K,
+                                         (int)(t * TILE_N) + (int)cta_rank * (TILE_N / 2), hint_x);
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================================== MMA issuer (leader CTA, one lane)
+        if (leader && lane == 0) {
+            uint32_t stage = 0, phase = 0, buf = 0, tphase = 0;
+            for (uint32_t t = slot; t < n_tiles; t += n_slots) {
+                mbar_wait(bar_tempty + 8 * buf, tphase ^ 1);       // both CTAs drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * TILE_N;
+                for (int kc = 0; kc < K_CHUNKS; ++kc) {
+                    mbar_wait(bar_full + 8 * stage, phase);        // both CTAs' bytes have landed
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * STAGE2_BYTES;
+                    const uint64_t adesc = make_desc_sw128(sa);
+                    const uint64_t bdesc = make_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < 4; ++k4)
+                        tc_mma_pair<TF32>(d_tmem, adesc + 2 * k4, bdesc + 2 * k4, IDESC, (kc | k4) != 0 ? 1u : 0u);
+                    tc_commit_pair(bar_empty + 8 * stage);          // frees the stage in both CTAs
+                    if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+                }
+                tc_commit_pair(bar_tfull + 8 * buf);                // accumulators ready in both CTAs
+                if (++buf == 2) { buf = 0; tphase ^= 1; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ============================================== epilogue (each CTA: its own 128 queries)
+        const uint32_t tempty_leader = map_to_cta(bar_tempty, 0);
+        epilogue_loop(m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
+                      partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp - 4, lane,
+                      [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); }, dbg);
+    }
+
+    tc_fence_before();
+    cluster_sync_all();                                    // nobody exits while the peer may still touch its smem / barriers
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
@@ -436,6 +638,8 @@ struct UmmaPlan {
     int device = 0;
     int sms = 148;
     bool attr_set = false;
+    int dbg = 0;                     // ORX_UMMA_DEBUG: timing experiments (results are garbage when set)
+    bool use_pairs = true;           // ORX_UMMA_PAIRS=0 keeps every batch on the 1-CTA kernel (A/B measurements)
     uint64_t *partial = nullptr;
     size_t partial_n = 0;
     float *floor = nullptr;
@@ -449,6 +653,10 @@ UmmaPlan *umma_plan_create(int device) {
     UmmaPlan *p = new UmmaPlan();
     p->device = device;
     cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
+    const char *env = getenv("ORX_UMMA_PAIRS");
+    if (env && env[0] == '0') p->use_pairs = false;
+    env = getenv("ORX_UMMA_DEBUG");
+    if (env) p->dbg = atoi(env);
     return p;
 }
 void umma_plan_destroy(UmmaPlan *p) {
@@ -489,15 +697,21 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
         cudaError_t e = cudaFuncSetAttribute(scan_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(scan_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(scan_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(scan_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL);
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
         p->attr_set = true;
     }
     constexpr int MAX_Q = 2048;              // 16 query tiles -> 9 row slots -> 144 CTAs
     for (int q0 = 0; q0 < nq; q0 += MAX_Q) {
         const int m = nq - q0 < MAX_Q ? nq - q0 : MAX_Q;
-        const int m_tiles = (m + TILE_M - 1) / TILE_M;
+        // batches beyond one query tile run on CTA pairs (cta_group::2, 256 queries per pair)
+        const bool pairs = m > TILE_M && p->use_pairs;
+        const int m_tiles = pairs ? (m + 2 * TILE_M - 1) / (2 * TILE_M) : (m + TILE_M - 1) / TILE_M;
         const uint32_t n_tiles = (n_rows + TILE_N - 1) / TILE_N;
-        int n_slots = p->sms / m_tiles;
+        int n_slots = (pairs ? p->sms / 2 : p->sms) / m_tiles;
         if (n_slots < 1) n_slots = 1;
         if ((uint32_t)n_slots > n_tiles) n_slots = (int)n_tiles;
         cudaError_t e = ensure_buf(p->partial, p->partial_n, (size_t)m * n_slots * CAND);
@@ -506,22 +720,33 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
         CUtensorMap map_q, map_x;
         const void *qbase = tf32 ? (const void *)(qhat + (size_t)q0 * ORX_DIM) : (const void *)(qhat16 + (size_t)q0 * ORX_DIM);
-        // qhat / qhat16 are padded with zero rows to a multiple of TILE_M by the caller (stage_queries)
-        if (!encode_map(&map_q, qbase, (uint64_t)m_tiles * TILE_M, tf32, TILE_M)) return ORX_ERR_CUDA;
-        if (!encode_map(&map_x, table, (uint64_t)n_rows, tf32, TILE_N)) return ORX_ERR_CUDA;
+        // qhat / qhat16 are padded with zero rows to a multiple of 256 by the caller (stage_queries)
+        if (!encode_map(&map_q, qbase, (uint64_t)((m + 255) / 256 * 256), tf32, TILE_M)) return ORX_ERR_CUDA;
+        if (!encode_map(&map_x, table, (uint64_t)n_rows, tf32, pairs ? TILE_N / 2 : TILE_N)) return ORX_ERR_CUDA;
         cudaMemsetAsync(p->gthr, 0, (size_t)m * sizeof(uint32_t), st);
         if (ev_begin && q0 == 0) cudaEventRecord(ev_begin, st);
-        const int grid = m_tiles * n_slots;
-        if (tf32)
-            scan_umma_kernel<true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                         k, margin, p->partial, p->floor, p->gthr);
-        else
-            scan_umma_kernel<false><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                          k, margin, p->partial, p->floor, p->gthr);
+        if (pairs) {
+            const int grid = 2 * m_tiles * n_slots;
+            if (tf32)
+                scan_umma2_kernel<true><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
+                                                                               k, margin, p->partial, p->floor, p->gthr, p->dbg);
+            else
+                scan_umma2_kernel<false><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
+                                                                                k, margin, p->partial, p->floor, p->gthr, p->dbg);
+        } else {
+            const int grid = m_tiles * n_slots;
+            if (tf32)
+                scan_umma_kernel<true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
+                                                                             k, margin, p->partial, p->floor, p->gthr, p->dbg);
+            else
+                scan_umma_kernel<false><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
+                                                                              k, margin, p->partial, p->floor, p->gthr, p->dbg);
+        }
         if (ev_end && q0 + MAX_Q >= nq) cudaEventRecord(ev_end, st);
         launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, 2, m,
                         k, n_rows, eps, out_ids + (size_t)q0 * k, out_dist + (size_t)q0 * k, out_counts + q0,
                         out_flags + q0, st, p->floor);
+        if (p->dbg) launch_flags_from_prep(prep + q0, m, out_flags + q0, st);   // timing experiments: no fallbacks
         *launch_counter += 2;
         e = cudaGetLastError();
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
