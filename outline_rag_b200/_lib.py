@@ -12,7 +12,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liborx.so")
+LIB_PATH = os.environ.get("ORX_LIB") or os.path.join(_HERE, "liborx.so")   # ORX_LIB: A/B builds side by side
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ORX_DIM = 1024
