@@ -74,6 +74,7 @@ void launch_flags_from_prep(const QueryPrep *prep, int nq, int *flags, cudaStrea
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int FIN_SURV = 256;          // survivors of the head-threshold filter (fast path)
+constexpr int FIN_SORT_MAX = 2048;     // keys the shared-memory bitonic sort takes (unsorted-list path)
 
 template <typename T, int S>
 __global__ void __launch_bounds__(FIN_THREADS)
@@ -146,6 +147,35 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
             __syncthreads();
         }
     }
+    __shared__ uint64_t s_all[FIN_SORT_MAX];
+    const int total_keys = nparts * K;
+    if (!fast && total_keys <= FIN_SORT_MAX) {
+        // 1c (unsorted lists that fit shared memory, i.e. the tcgen05 scan at large batches): bitonic sort
+        //     of all keys, descending; the first K are the query's candidates.
+        int n = 64;
+        while (n < total_keys) n <<= 1;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += FIN_THREADS) s_all[i] = i < total_keys ? partial[i] : 0ull;
+        __syncthreads();
+        for (int size = 2; size <= n; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = threadIdx.x; i < (n >> 1); i += FIN_THREADS) {
+                    const int lo = 2 * i - (i & (stride - 1));          // index with bit `stride` clear
+                    const int hi = lo + stride;
+                    const uint64_t a = s_all[lo], b = s_all[hi];
+                    const bool desc = (lo & size) == 0;                // descending overall
+                    if ((a < b) == desc) {
+                        s_all[lo] = b;
+                        s_all[hi] = a;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (threadIdx.x < K) s_keys[0][threadIdx.x] = s_all[threadIdx.x];
+        __syncthreads();
+        fast = true;
+    }
     if (!fast) {
         // 1b (generic): each warp folds lists warp, warp+16, ... into a register-resident sorted
         //     top-K (offer_lanes takes unsorted input), then a tree merge through shared memory.
@@ -170,13 +200,28 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     }
     const uint64_t *s_cand = s_keys[0];
 
-    // 2. canonical rescore, one warp per candidate
+    // 2. canonical rescore, one warp per candidate.  Coarse (tcgen05) candidates that are more than the
+    //    margin below the k-th best COARSE score cannot reach the top-k (same argument as the scan's
+    //    running threshold), so they are not rescored; the proof below accounts for them through `cut`.
+    __shared__ unsigned char s_ok[K];
     const float *q = q_all + (size_t)qi * ORX_DIM;
     const double n2q = prep[qi].n2q;
+    float cut = __int_as_float(0xff800000);               // -inf: nothing is cut
+    if (floor_all != nullptr) {
+        // s_cand is sorted by key, descending: untrusted (ORD_ALWAYS) rows first, then by coarse score;
+        // the cut hangs on the k-th best REGULAR candidate
+        int n_always = 0;
+        for (int c = 0; c < K; ++c) n_always += (key_ord(s_cand[c]) == ORD_ALWAYS);
+        const int kth = n_always + k - 1;
+        const uint32_t ok_ord = kth < K ? key_ord(s_cand[kth]) : 0u;
+        if (ok_ord != 0u) cut = ord_to_float(ok_ord) - (float)(2.0 * eps + 1e-6);
+    }
     for (int c = warp; c < K; c += FIN_WARPS) {
         const uint64_t key = s_cand[c];
-        if (key == 0ull) {                    // empty slot: sorts after everything
+        const bool skip = key == 0ull || (key_ord(key) != ORD_ALWAYS && ord_to_float(key_ord(key)) <= cut);
+        if (skip) {                           // empty or cut: sorts after everything, never output
             if (lane == 0) {
+                s_ok[c] = 0;
                 s_dist[c] = __longlong_as_double(0x7ff8000000000000ll);
                 s_hi[c] = ~0ull;
                 s_lo[c] = ~0ull;
@@ -188,6 +233,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         const orx_id id = row_ids[row];
         const double dot = warp_canon_dot<T>(table + (size_t)row * ORX_DIM, q, lane);
         if (lane == 0) {
+            s_ok[c] = 1;
             s_dist[c] = canon_dist(dot, n2x, n2q);
             s_hi[c] = id.hi;
             s_lo[c] = id.lo;
@@ -199,12 +245,12 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     // 3. order by (distance ASC, NaN last, id ASC): rank by counting
     const int t = threadIdx.x;
     const int count = min(k, s_valid);
-    if (t < K && s_cand[t] != 0ull) {
+    if (t < K && s_ok[t]) {
         int rank = 0;
         const double d = s_dist[t];
         const uint64_t hi = s_hi[t], lo = s_lo[t];
         for (int c = 0; c < K; ++c)
-            rank += (c != t && s_cand[c] != 0ull && sorts_before(s_dist[c], s_hi[c], s_lo[c], d, hi, lo));
+            rank += (c != t && s_ok[c] && sorts_before(s_dist[c], s_hi[c], s_lo[c], d, hi, lo));
         if (rank < k) {
             out_ids[(size_t)qi * k + rank].hi = hi;
             out_ids[(size_t)qi * k + rank].lo = lo;
@@ -238,6 +284,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                 // zero-norm rows are never collected by the coarse pass: too few finite rows -> exact scan
                 if (count == k) {
                     double bound = ord_last == ORD_NAN ? -1.0e30 : (double)ord_to_float(ord_last);
+                    if ((double)cut > bound) bound = (double)cut;      // candidates that were not rescored
                     for (int p = 0; p < nparts; ++p) {
                         const double f = (double)floor_all[(size_t)qi * nparts + p];
                         if (!(f <= bound)) bound = f;  // also catches NaN / +inf (overflowed list)
