@@ -343,10 +343,20 @@ def run_ours(a):
             ok &= bool((np.diff(dist_h[qi]) >= 0).all())
         verify = {"sampled_rescoring_bit_exact": ok, "queries_checked": min(a.verify, B)}
 
-    if rank != 0:
+    def shutdown():
+        # every rank has finished its last search before any exchange buffer is unmapped
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if twin is not None:
+            twin.local.close()
+        ix.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
 
     hbm_peak, tensor_peak, peak_src = measured_peaks()
@@ -393,9 +403,7 @@ def run_ours(a):
     if not a.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = time_cpu_replica(a.rows, a.cpu_sample_rows, B, 5, budget_s=15.0)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    shutdown()
 
 
 def run_mixed(a):

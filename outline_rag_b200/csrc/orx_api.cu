@@ -163,9 +163,6 @@ struct orx_index {
     DevBuf<__nv_bfloat16> qhat16;
     DevBuf<orx::QueryPrep> prep;
     DevBuf<uint64_t> partial;
-    DevBuf<orx_id> res_ids;
-    DevBuf<double> res_dist;
-    DevBuf<int> res_counts, res_flags;
     PinBuf<float> h_q;
     PinBuf<orx::QueryPrep> h_prep;
     PinBuf<orx_id> h_ids;
@@ -183,7 +180,6 @@ struct orx_index {
     PinBuf<uint32_t> h_u32a, h_u32b;
     PinBuf<int> h_flag;
 
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     std::vector<cudaEvent_t> scan_ev;   // pairs bracketing each scan launch of the current search
     size_t scan_ev_used = 0;
     orx::UmmaPlan *umma = nullptr;
@@ -660,13 +656,6 @@ int orx_create(orx_index **out, int dim, int dtype, uint64_t capacity_rows, int 
         orx_destroy(ix);
         return rc;
     }
-    for (auto &e : ix->ev) {
-        cudaError_t ce = cudaEventCreate(&e);
-        if (ce != cudaSuccess) {
-            orx_destroy(ix);
-            return fail(ORX_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(ce));
-        }
-    }
     ix->umma = orx::umma_plan_create(device);
     ix->host_row_ids.reserve(cap);
     ix->map.reserve(cap);
@@ -684,14 +673,11 @@ void orx_destroy(orx_index *ix) {
     cudaFree(ix->n2);
     cudaFree(ix->row_ids);
     ix->q_dev.release(); ix->qhat.release(); ix->qhat16.release(); ix->prep.release(); ix->partial.release();
-    ix->res_ids.release(); ix->res_dist.release(); ix->res_counts.release(); ix->res_flags.release();
     ix->h_q.release(); ix->h_prep.release(); ix->h_ids.release(); ix->h_dist.release();
     ix->h_counts.release(); ix->h_flags.release();
     ix->fb_list.release(); ix->fb_count.release(); ix->fb_dist.release();
     ix->stage.release(); ix->d_src_idx.release(); ix->d_dst_row.release(); ix->d_ids.release();
     ix->d_flag.release(); ix->h_u32a.release(); ix->h_u32b.release(); ix->h_flag.release();
-    for (auto &e : ix->ev)
-        if (e) cudaEventDestroy(e);
     for (auto &e : ix->scan_ev) cudaEventDestroy(e);
     if (ix->xchg) {
         Exchange *x = ix->xchg;

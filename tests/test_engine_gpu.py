@@ -482,3 +482,48 @@ def test_snapshot_roundtrip_is_bit_identical(Index, small_table, tmp_path, dtype
     v.flush()
     with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
         orx.Index.load(str(tmp_path / "snap"))
+
+
+def test_concurrent_threads_search_while_a_writer_refreshes(Index, small_table):
+    """The uvicorn worker runs searches and the refresh task interleaved (asyncio.to_thread): calls on one
+    index are serialised, every search sees a consistent table (either before or after a whole batch)."""
+    import threading
+    X, Q, _ = small_table
+    n = 4000
+    ids = _ids(n)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X[:n])
+        want_before = [O.topk_exact(X[:n], ids, Q[i], K)[0] for i in range(4)]
+        Xa = X[:n].copy()
+        Xa[:200] = X[n:n + 200]
+        want_after = [O.topk_exact(Xa, ids, Q[i], K)[0] for i in range(4)]
+        errors, seen = [], {"before": 0, "after": 0}
+
+        def reader(i):
+            try:
+                for _ in range(30):
+                    got = ix.search(Q[i], K)[0][0]
+                    if np.array_equal(got, want_before[i]):
+                        seen["before"] += 1
+                    elif np.array_equal(got, want_after[i]):
+                        seen["after"] += 1
+                    else:
+                        errors.append("inconsistent result")
+            except Exception as e:      # noqa: BLE001
+                errors.append(repr(e))
+
+        def writer():
+            try:
+                ix.upsert(ids[:200], X[n:n + 200])         # in-place replacement of 200 rows, one batch
+            except Exception as e:      # noqa: BLE001
+                errors.append(repr(e))
+
+        threads = [threading.Thread(target=reader, args=(i,)) for i in range(4)] + [threading.Thread(target=writer)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors[:3]
+        assert seen["before"] + seen["after"] == 120
+        got = ix.search(Q[:4], K)[0]
+        assert all(np.array_equal(got[i], want_after[i]) for i in range(4))
