@@ -527,3 +527,44 @@ def test_concurrent_threads_search_while_a_writer_refreshes(Index, small_table):
         assert seen["before"] + seen["after"] == 120
         got = ix.search(Q[:4], K)[0]
         assert all(np.array_equal(got[i], want_after[i]) for i in range(4))
+
+
+def test_more_queries_than_one_tcgen05_launch_takes(Index, synth100k):
+    """nq > 2048 is split into several tcgen05 launches (and > 1024 into several exchange rounds)."""
+    n, nq = 5000, 2100
+    X = synth100k.table(n)
+    rng = np.random.default_rng(5)
+    Q = (X[rng.integers(0, n, size=nq)] + 0.2 * rng.standard_normal((nq, DIM))).astype(np.float32)
+    ids = _ids(n)
+    with Index("bf16") as ix:
+        ix.upsert(ids, X)
+        g_ids, g_d, g_c = ix.search(Q, K)
+        assert ix.stats()["last_path"] == 2
+        ix.shard_connect([ix.shard_export(1, 0)])
+        s_ids, s_d, s_c = ix.search_sharded(Q, K)
+    assert np.array_equal(g_ids, s_ids) and np.array_equal(g_d.view(np.uint64), s_d.view(np.uint64))
+    rows = stored_bf16_rows(X)
+    for i in list(range(0, nq, 97)) + [2047, 2048, 2099]:
+        w_ids, w_d = O.topk_exact(rows, ids, Q[i], K)
+        assert np.array_equal(g_ids[i], w_ids) and np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64)), i
+    assert (g_c == K).all()
+
+
+def test_host_upsert_larger_than_one_staging_chunk(Index, synth100k):
+    """70 000 host rows = two 65 536-row staging chunks; a NaN in the SECOND chunk rejects the whole batch."""
+    import outline_rag_b200 as orx
+    n = 70_000
+    X = synth100k.table(n)
+    ids = _ids(n)
+    Q, _ = synth100k.queries(3, n)
+    with Index("fp32", capacity=1024) as ix:
+        bad = X.copy()
+        bad[69_000, 17] = np.nan
+        with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
+            ix.upsert(ids, bad)
+        assert len(ix) == 0
+        ix.upsert(ids, X)
+        assert len(ix) == n
+        got, found = ix.fetch(ids[[0, 65_535, 65_536, 69_999]])
+        assert found.all() and np.array_equal(got.view(np.uint32), X[[0, 65_535, 65_536, 69_999]].view(np.uint32))
+        _check_exact(ix, X, ids, Q)
