@@ -148,6 +148,13 @@ def time_cpu_replica(rows_full: int, sample_rows: int, batch: int, n_queries: in
     full table by rows (the scan is linear in rows)."""
     from oracle import cosine_topk as O
     from outline_rag_b200.synth import Synth, default_centres
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is entitled to every host core it can use
+    n_cores = len(os.sched_getaffinity(0))
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=n_cores)
+    except Exception:
+        pass
     sample_rows = min(sample_rows, rows_full)
     syn = Synth(default_centres(rows_full))
     X = syn.table(sample_rows)
