@@ -102,6 +102,16 @@ int orx_contains(const orx_index *idx, orx_id id);
 int orx_search(orx_index *idx, const float *queries, int nq, int dim, int k,
                orx_id *out_ids, double *out_dist, int *out_counts);
 
+/* The same query restricted to a set of chunk ids -- the SQL with a WHERE clause, i.e. what the
+ * upstream store's `filter=` argument compiles to after the metadata predicate has been resolved to
+ * `langchain_id`s (e.g. `source_id = ANY(...)`, reference app/rag.py:216-224 shows that look-up).
+ * allow_ids [n_allow] host; unknown ids are ignored, duplicates count once.  Every eligible row is
+ * rescored canonically (no coarse pass), so the result is exact by construction; cost is
+ * O(n_allow) row reads per query.  Same outputs and ordering as orx_search. */
+int orx_search_filtered(orx_index *idx, const float *queries, int nq, int dim, int k,
+                        const orx_id *allow_ids, uint64_t n_allow,
+                        orx_id *out_ids, double *out_dist, int *out_counts);
+
 /* Merge `n_lists` per-shard results (each [nq, k] as written by orx_search, all on
  * this index's device or all on the host) into the global top-k with the same
  * ordering.  The on-device step after the NCCL allgather of the row-sharded path. */

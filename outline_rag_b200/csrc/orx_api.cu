@@ -894,6 +894,74 @@ int orx_search(orx_index *ix, const float *queries, int nq, int dim, int k, orx_
     return search_locked(ix, queries, nq, k, out_ids, out_dist, out_counts);
 }
 
+int orx_search_filtered(orx_index *ix, const float *queries, int nq, int dim, int k, const orx_id *allow_ids,
+                        uint64_t n_allow, orx_id *out_ids, double *out_dist, int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "different vector dimensions %d and %d", ORX_DIM, dim);
+    if (k < 1 || k > ORX_MAX_K) return fail(ORX_ERR_INVALID, "k must be in [1, %d], got %d", ORX_MAX_K, k);
+    if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
+    if (nq == 0) return ORX_OK;
+    if (!queries || !out_ids || !out_dist || !out_counts || (n_allow && !allow_ids)) return fail(ORX_ERR_INVALID, "null argument");
+    if (is_device_ptr(allow_ids)) return fail(ORX_ERR_INVALID, "allow_ids must be a host pointer");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    cudaStream_t st = ix->stream;
+    const bool out_on_dev = is_device_ptr(out_ids);
+    if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
+        return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
+    const size_t nk = (size_t)nq * k;
+    // the eligible rows: ids that are live, each row once (the WHERE clause of the SQL)
+    std::vector<uint32_t> rows;
+    rows.reserve(n_allow);
+    for (uint64_t i = 0; i < n_allow; ++i) {
+        auto it = ix->map.find(allow_ids[i]);
+        if (it != ix->map.end()) rows.push_back(it->second);
+    }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+    const uint32_t m = (uint32_t)rows.size();
+
+    const float *q_src = nullptr;
+    int rc = stage_queries(ix, queries, nq, &q_src);
+    if (rc != ORX_OK) return rc;
+    CK(ix->h_prep.ensure(nq));
+    CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
+    if (!out_on_dev) {
+        CK(ix->h_ids.ensure(nk));
+        CK(ix->h_dist.ensure(nk));
+        CK(ix->h_counts.ensure(nq));
+    }
+    SearchOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                  out_on_dev ? out_counts : ix->h_counts.p};
+    CK(ix->fb_list.ensure(std::max<size_t>(m, 1)));
+    CK(ix->fb_dist.ensure(std::max<size_t>(m, 1)));
+    CK(ix->fb_count.ensure(1));
+    if (m) CK(cudaMemcpyAsync(ix->fb_list.p, rows.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ix->fb_count.p, &m, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    // few rows: no scan at all -- every eligible row is rescored canonically and the k best are selected
+    for (int j = 0; j < nq; ++j) {
+        if (m)
+            orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)j * ORX_DIM, ix->prep.p + j,
+                                     ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, st);
+        orx::launch_select_list(ix->row_ids, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, k, out.ids + (size_t)j * k,
+                                out.dist + (size_t)j * k, out.counts + j, st);
+        ix->stats.kernel_launches += m ? 2 : 1;
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int j = 0; j < nq; ++j)
+        if (ix->h_prep.p[j].nonfinite)
+            return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+    if (!out_on_dev) {
+        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
+        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
+        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
+    }
+    ix->stats.searches += 1;
+    ix->stats.queries += nq;
+    return ORX_OK;
+}
+
 int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids, const double *dist,
                    const int *counts, orx_id *out_ids, double *out_dist, int *out_counts) {
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");

@@ -196,6 +196,19 @@ class Index:
                              C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
         return ids, dist, cnt
 
+    def search_filtered(self, queries, k: int, allow_ids):
+        """Exact top-k among the given chunk ids only (`WHERE langchain_id IN (...)`); NumPy in/out."""
+        q = _host_f32(queries, "queries")
+        nq, dim = q.shape
+        allow = ids_to_array(allow_ids)
+        ids = np.zeros((nq, max(k, 0), 2), np.uint64)
+        dist = np.full((nq, max(k, 0)), np.nan, np.float64)
+        cnt = np.zeros(nq, np.int32)
+        check(lib.orx_search_filtered(self._h, C.c_void_p(q.ctypes.data), nq, dim, int(k),
+                                      C.c_void_p(allow.ctypes.data), allow.shape[0], C.c_void_p(ids.ctypes.data),
+                                      C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
+        return ids, dist, cnt
+
     def search_into(self, queries, k: int, ids_out, dist_out, counts_out) -> None:
         """`search` of a float32 CUDA tensor writing into caller-owned CUDA tensors (views of one
         result block in the row-sharded path: no allocation, no packing kernels)."""

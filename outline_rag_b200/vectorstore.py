@@ -60,6 +60,37 @@ class MemoryDocStore:
         for i in ids:
             self._rows.pop(i, None)
 
+    def ids_for_filter(self, flt: dict) -> list[str]:
+        """Resolve a metadata predicate to chunk ids -- `SELECT langchain_id ... WHERE <filter>` in
+        production.  Supported: {"col": value}, {"col": {"$in": [...]}}, {"col": {"$eq": v}},
+        {"$and": [f1, f2, ...]}, {"$or": [...]} (the subset of the upstream filter grammar that a
+        `source_id` / `title` / `url` predicate needs)."""
+        def match(meta: dict, f: dict) -> bool:
+            for key, cond in f.items():
+                if key == "$and":
+                    if not all(match(meta, c) for c in cond):
+                        return False
+                elif key == "$or":
+                    if not any(match(meta, c) for c in cond):
+                        return False
+                elif isinstance(cond, dict):
+                    v = meta.get(key)
+                    for op, arg in cond.items():
+                        if op == "$in":
+                            ok = v in arg
+                        elif op == "$eq":
+                            ok = v == arg
+                        elif op == "$ne":
+                            ok = v != arg
+                        else:
+                            raise NotImplementedError(f"filter operator {op}")
+                        if not ok:
+                            return False
+                elif meta.get(key) != cond:
+                    return False
+            return True
+        return [i for i, (_, m) in self._rows.items() if match(m, flt)]
+
     def ids_for_source(self, source_ids: Iterable[str]) -> list[str]:
         """``SELECT langchain_id ... WHERE source_id = ANY(:ids)`` (reference app/rag.py:216-224)."""
         want = set(source_ids)
@@ -189,9 +220,13 @@ class GpuVectorStore:
 
     def similarity_search_with_score_by_vector(self, embedding, k: int = 4, filter=None, **_: Any):
         """-> ``[(Document, cosine distance)]`` ascending, exactly the SQL's ORDER BY ... LIMIT k."""
+        q = np.asarray(embedding, dtype=np.float32).reshape(1, -1)
         if filter is not None:
-            raise NotImplementedError("metadata filters are not pushed into the scan yet (SURVEY.md 8f-4)")
-        ids, dist, cnt = self.index.search(np.asarray(embedding, dtype=np.float32).reshape(1, -1), k)
+            # the metadata predicate is resolved where the metadata lives (doc store / Postgres), the
+            # similarity ordering of the eligible chunks runs on the GPU (orx_search_filtered)
+            ids, dist, cnt = self.index.search_filtered(q, k, self.doc_store.ids_for_filter(filter))
+        else:
+            ids, dist, cnt = self.index.search(q, k)
         return self._hydrate(ids[0], dist[0], int(cnt[0]))
 
     def batch_search_by_vector(self, embeddings, k: int = 4):

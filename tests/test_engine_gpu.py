@@ -568,3 +568,33 @@ def test_host_upsert_larger_than_one_staging_chunk(Index, synth100k):
         got, found = ix.fetch(ids[[0, 65_535, 65_536, 69_999]])
         assert found.all() and np.array_equal(got.view(np.uint32), X[[0, 65_535, 65_536, 69_999]].view(np.uint32))
         _check_exact(ix, X, ids, Q)
+
+
+def test_filtered_search_is_the_sql_with_a_where_clause(Index, small_table):
+    import outline_rag_b200 as orx
+    X, Q, _ = small_table
+    n = 3000
+    X = X[:n].copy()
+    X[77] = 0.0                                                # an eligible zero-norm row sorts last
+    ids = _ids(n, 500)
+    rng = np.random.default_rng(8)
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        for m in (0, 1, 5, 12, 40, 700):
+            sel = np.sort(rng.choice(n, size=m, replace=False)) if m else np.zeros(0, np.int64)
+            if m >= 5:
+                sel[0] = 77
+                sel = np.unique(sel)
+            allow = np.concatenate([ids[sel], ids[sel][:3], O.ids_from_ints([7, 8])]) if m else O.ids_from_ints([7])
+            g_ids, g_d, g_c = ix.search_filtered(Q[:3], K, allow)          # duplicates + unknown ids are harmless
+            for i in range(3):
+                w_ids, w_d = O.topk_exact(X[sel], ids[sel], Q[i], K, exhaustive=True)
+                mm = len(w_d)
+                assert g_c[i] == mm
+                assert np.array_equal(g_ids[i, :mm], w_ids)
+                assert np.array_equal(g_d[i, :mm].view(np.uint64), w_d.view(np.uint64))
+                assert np.isnan(g_d[i, mm:]).all()
+        bad = Q[:1].copy()
+        bad[0, 0] = np.nan
+        with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
+            ix.search_filtered(bad, K, ids[:5])

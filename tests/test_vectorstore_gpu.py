@@ -90,3 +90,29 @@ def test_errors_propagate_like_the_reference(synth100k):
         store.add_documents([orx.Document(page_content="row:1")])
     assert len(store.index) == 0
     store.index.close()
+
+
+def test_metadata_filter_restricts_the_candidates(synth100k):
+    """`filter=` (upstream VectorStore argument): predicate -> ids in the doc store, ordering on the GPU."""
+    import uuid
+    import outline_rag_b200 as orx
+    n, per_doc = 2000, 20
+    emb = FakeBgeM3(synth100k, n)
+    store = orx.GpuVectorStore.create_sync(emb)
+    docs = [orx.Document(page_content=f"row:{i}", metadata={"source_id": f"doc{i // per_doc}", "title": f"t{i % 3}"},
+                         id=str(uuid.UUID(int=i))) for i in range(n)]
+    store.add_documents(docs)
+    q = emb.embed_query("q:3")
+    X = synth100k.table(n)
+    ids = O.ids_arange(0, n)
+    for flt, keep in [({"source_id": "doc7"}, [i for i in range(n) if i // per_doc == 7]),
+                      ({"source_id": {"$in": ["doc1", "doc2", "doc50"]}}, [i for i in range(n) if i // per_doc in (1, 2, 50)]),
+                      ({"$and": [{"source_id": {"$in": ["doc1", "doc2"]}}, {"title": "t0"}]},
+                       [i for i in range(n) if i // per_doc in (1, 2) and i % 3 == 0]),
+                      ({"source_id": "no-such-doc"}, [])]:
+        got = store.similarity_search_with_score_by_vector(q, k=12, filter=flt)
+        keep = np.asarray(keep, np.int64)
+        w_ids, w_d = O.topk_exact(X[keep], ids[keep], np.asarray(q, np.float32), 12, exhaustive=True)
+        assert [d.id for d, _ in got] == [str(uuid.UUID(int=v)) for v in O.ids_to_ints(w_ids)]
+        assert [s for _, s in got] == w_d.tolist()
+    store.index.close()
