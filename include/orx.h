@@ -26,7 +26,8 @@ extern "C" {
 #endif
 
 #define ORX_DIM 1024            /* VECTOR_DIM, reference app/config.py:8 */
-#define ORX_MAX_K 32            /* TOP_K is 12, reference app/config.py:253 */
+#define ORX_MAX_K 128           /* TOP_K is 12 (reference app/config.py:253); up to 128 for a wider
+                                   reranker feed.  k > 32 always runs the fp32 scan. */
 
 #define ORX_DTYPE_F32 0         /* rows stored verbatim (fp32) + per-row 1/norm   */
 #define ORX_DTYPE_BF16 1        /* rows stored as RNE-bf16 of the normalised row  */

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("ORX_LIB") or os.path.join(_HERE, "liborx.so")   # ORX
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ORX_DIM = 1024
-ORX_MAX_K = 32
+ORX_MAX_K = 128
 ORX_IPC_HANDLE_BYTES = 64
 DTYPE_F32 = 0
 DTYPE_BF16 = 1

@@ -20,7 +20,7 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import ORX_DIM, ORX_ERR_DIM, ORX_ERR_NONFINITE, OrxValueError
+from ._lib import ORX_DIM, ORX_ERR_DIM, ORX_ERR_NONFINITE, ORX_MAX_K, OrxValueError
 
 
 class QueryBatcher:
@@ -46,8 +46,8 @@ class QueryBatcher:
         if not np.isfinite(q).all():
             fut.set_exception(OrxValueError(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector"))
             return await fut
-        if not (1 <= int(k) <= 32):
-            fut.set_exception(OrxValueError(-1, f"k must be in [1, 32], got {k}"))
+        if not (1 <= int(k) <= ORX_MAX_K):
+            fut.set_exception(OrxValueError(-1, f"k must be in [1, {ORX_MAX_K}], got {k}"))
             return await fut
         self._pending.append((q, int(k), fut))
         if len(self._pending) >= self.max_batch:

@@ -41,7 +41,7 @@ void launch_publish(const void *my_slot, void *const *peer_slot, uint32_t *const
                                           (int)(bytes / 16), seq);
 }
 
-constexpr int XMERGE_MAX = 512;
+constexpr int XMERGE_MAX = 1024;      // world * k candidates per query (8 GPUs x k = 128)
 
 __global__ void __launch_bounds__(256)
 merge_wait_kernel(int world, int rank, int nq, int k, const char *__restrict__ set_base, size_t slot_stride,

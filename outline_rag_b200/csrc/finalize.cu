@@ -308,14 +308,16 @@ static void launch_finalize_t(const void *table, const double *n2, const orx_id 
                               int k, uint32_t n_rows, double eps, orx_id *out_ids, double *out_dist,
                               int *out_counts, int *out_flags, cudaStream_t st, const float *floor) {
     const T *tab = static_cast<const T *>(table);
-    if (slots == 1)
-        finalize_kernel<T, 1><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
-                                                          eps, out_ids, out_dist, out_counts, out_flags, floor,
-                                                          floor == nullptr);
-    else
-        finalize_kernel<T, 2><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows,
-                                                          eps, out_ids, out_dist, out_counts, out_flags, floor,
-                                                          floor == nullptr);
+#define ORX_FIN(S_)                                                                                          \
+    finalize_kernel<T, S_><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows, eps, \
+                                                       out_ids, out_dist, out_counts, out_flags, floor, floor == nullptr)
+    switch (slots) {
+        case 1: ORX_FIN(1); break;
+        case 2: ORX_FIN(2); break;
+        case 4: ORX_FIN(4); break;
+        default: ORX_FIN(5); break;
+    }
+#undef ORX_FIN
 }
 
 void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,

@@ -13,7 +13,8 @@ constexpr double EPS_UMMA_TF32 = 2.5e-3;  // both operands cut to 10 mantissa bi
 constexpr double EPS_UMMA_BF16 = 2.5e-3;  // RNE bf16 query: 2^-9 = 1.96e-3 (rows are exact bf16), + accumulation
 
 // candidate list = 32 * slots keys per query: k <= 16 -> 32 candidates, k <= 32 -> 64
-inline int slots_for_k(int k) { return k <= 16 ? 1 : 2; }
+// candidate list = 32 * slots keys per query: k <= 16 -> 32, k <= 32 -> 64, k <= 128 -> 32 more than k at least
+inline int slots_for_k(int k) { return k <= 16 ? 1 : k <= 32 ? 2 : k <= 96 ? 4 : 5; }
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 

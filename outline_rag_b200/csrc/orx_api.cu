@@ -372,7 +372,7 @@ int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_s
 // ---- the scan + finalize of all nq queries (tcgen05 for batches, GEMV otherwise); *path = 1 / 2
 int scan_pass(orx_index *ix, const float *q_src, int nq, int k, const SearchOut &out, int *flags, int *path) {
     const uint32_t n_rows = (uint32_t)ix->n_live;
-    if (ix->umma && orx::umma_should_use(ix->umma, nq, n_rows)) {
+    if (ix->umma && k <= 32 && orx::umma_should_use(ix->umma, nq, n_rows)) {
         *path = 2;
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
@@ -1090,7 +1090,7 @@ int orx_shard_export(orx_index *ix, int world, int rank, void *handle_out) {
     Exchange *x = new Exchange();
     x->world = world;
     x->rank = rank;
-    x->slot_bytes = slot_layout(XQ_MAX, ORX_MAX_K).bytes;
+    x->slot_bytes = slot_layout(XQ_MAX, 32).bytes;          // nq * k <= XQ_MAX * 32 per exchange round
     x->set_bytes = x->slot_bytes * world;
     x->flags_off = 2 * x->set_bytes;
     x->total_bytes = x->flags_off + 2 * (size_t)world * XFLAG_STRIDE;
@@ -1164,8 +1164,10 @@ int orx_search_sharded(orx_index *ix, const float *queries, int nq, int dim, int
     DeviceGuard g(ix->device);
     if (!ix->xchg || !ix->xchg->connected) return fail(ORX_ERR_INVALID, "shard exchange not connected (orx_shard_export / orx_shard_connect)");
     const bool q_dev = is_device_ptr(queries), o_dev = is_device_ptr(out_ids);
-    for (int q0 = 0; q0 < nq; q0 += XQ_MAX) {      // every rank chunks identically
-        const int m = std::min(XQ_MAX, nq - q0);
+    if ((size_t)ix->xchg->world * k > 1024) return fail(ORX_ERR_INVALID, "sharded search: world * k must be <= 1024");
+    const int qchunk = k <= 32 ? XQ_MAX : XQ_MAX * 32 / k;       // a slot holds XQ_MAX queries at k <= 32
+    for (int q0 = 0; q0 < nq; q0 += qchunk) {       // every rank chunks identically
+        const int m = std::min(qchunk, nq - q0);
         (void)q_dev; (void)o_dev;
         int rc = search_sharded_locked(ix, ix->xchg, queries + (size_t)q0 * ORX_DIM, m, k, out_ids + (size_t)q0 * k,
                                        out_dist + (size_t)q0 * k, out_counts + q0);

@@ -83,7 +83,9 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
         for (int i = 0; i < TOTAL; ++i) rank += (all[i] > mine);
         if (rank < K) partial[rank] = mine;
     }
-    const int nnz = __syncthreads_count(nonzero != 0) + (TOTAL > SCAN_THREADS ? __syncthreads_count(nonzero == 2) : 0);
+    int nnz = 0;                                     // total non-empty keys = sum_j #{threads holding >= j}
+#pragma unroll
+    for (int j = 1; j <= TOTAL / SCAN_THREADS; ++j) nnz += __syncthreads_count(nonzero >= j);
     if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
 }
 
@@ -102,10 +104,12 @@ static void launch_scan_gemv_t(const void *table, const float *scale, uint32_t n
                                int nq, int slots, uint64_t *partial, int grid, cudaStream_t st) {
     dim3 g(grid, nq);
     const T *tab = static_cast<const T *>(table);
-    if (slots == 1)
-        scan_gemv_kernel<T, 1><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial);
-    else
-        scan_gemv_kernel<T, 2><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial);
+    switch (slots) {
+        case 1: scan_gemv_kernel<T, 1><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
+        case 2: scan_gemv_kernel<T, 2><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
+        case 4: scan_gemv_kernel<T, 4><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
+        default: scan_gemv_kernel<T, 5><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
+    }
 }
 
 void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t n_rows,

@@ -676,7 +676,7 @@ const char *umma_last_error() { return g_umma_err.c_str(); }
 
 bool umma_should_use(const UmmaPlan *p, int nq, uint32_t n_rows) {
     // one table pass for the whole batch beats nq GEMV passes as soon as nq >= 2
-    return p != nullptr && nq >= 2 && n_rows >= 4096;
+    return p != nullptr && nq >= 2 && n_rows >= 4096;     // (k <= 32 is checked by the caller: 64-slot lists)
 }
 
 template <typename T>

@@ -94,7 +94,7 @@ def test_query_batches(Index, small_table, nq):
         _check_exact(ix, X[:4096], ids, Qb)
 
 
-@pytest.mark.parametrize("k", [1, 2, 12, 16, 17, 32])
+@pytest.mark.parametrize("k", [1, 2, 12, 16, 17, 32, 33, 64, 96, 100, 128])
 def test_all_k(Index, small_table, k):
     X, Q, _ = small_table
     ids = _ids(3000)
@@ -284,7 +284,7 @@ def test_ka8_input_errors(Index, small_table):
         qbad[1, 0] = np.nan
         with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
             ix.search(qbad, K)
-        for k in (0, 33, -1):
+        for k in (0, 129, -1):
             with pytest.raises(orx.OrxValueError):
                 ix.search(Q[:1], k)
         _check_exact(ix, X[:10], _ids(10), Q[:2])             # still healthy afterwards
@@ -598,3 +598,29 @@ def test_filtered_search_is_the_sql_with_a_where_clause(Index, small_table):
         bad[0, 0] = np.nan
         with pytest.raises(orx.OrxValueError, match="NaN or infinite"):
             ix.search_filtered(bad, K, ids[:5])
+
+
+def test_large_k_for_a_wider_reranker_feed(Index, small_table):
+    """k up to 128 (SURVEY.md 8f-4): batches stay exact (fp32 scan per query), ties and short tables too;
+    the sharded exchange chunks the batch so that a slot still fits."""
+    X, Q, _ = small_table
+    n = 6000
+    Xd = X[:n].copy()
+    Xd[100:260] = Xd[5]                                        # 160 identical rows: wider than k
+    ids = _ids(n)
+    with Index("fp32") as ix:
+        ix.upsert(ids, Xd)
+        _check_exact(ix, Xd, ids, np.concatenate([Q[:5], Xd[5:6]]), k=100)
+        assert ix.stats()["last_path"] == 1
+        ix.shard_connect([ix.shard_export(1, 0)])
+        a = ix.search(Q[:9], 128)
+        b = ix.search_sharded(Q[:9], 128)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+        # two disjoint 64-entry lists (even / odd ranks of the top-128) merge back to the top-64
+        m = ix.merge_topk(np.stack([a[0][:, 0::2], a[0][:, 1::2]]), np.stack([a[1][:, 0::2], a[1][:, 1::2]]),
+                          np.stack([np.full(9, 64, np.int32)] * 2), 64)
+        assert np.array_equal(m[0], a[0][:, :64]) and np.array_equal(m[1].view(np.uint64), a[1][:, :64].view(np.uint64))
+    with Index("bf16") as ix:
+        ix.upsert(ids[:50], Xd[:50])
+        g = ix.search(Q[:2], 128)
+        assert (g[2] == 50).all()
