@@ -1,0 +1,224 @@
+"""One device table, several worker processes (second half).
+
+The reference starts `uvicorn --workers ${UVICORN_WORKERS:-2}` (reference app/entrypoint.sh:16-18)
+and every worker PROCESS builds its own `rag.vector_store` handle onto the shared Postgres
+(reference app/rag.py:36-44).  A GPU-resident table must have ONE owner, so the owner runs
+`IndexServer` (an asyncio unix-socket server around one `Index`) and every worker talks to it
+through `RemoteIndex`, which has the same `search / upsert / delete / __len__` surface as
+`Index` and can be handed to `GpuVectorStore` as its index.
+
+Searches arriving from different workers within the batching window are coalesced by the
+server's `QueryBatcher` into one tcgen05 scan -- cross-process micro-batching for free.
+Writes are applied in arrival order on the owner's single stream, so a search issued after an
+upsert was acknowledged sees it (same guarantee as in-process use).
+
+Wire format: 4-byte big-endian length + msgpack map {"op", ...}; arrays travel as raw bytes with
+shape / dtype fields.  Errors come back as {"err": code, "msg": text} and are re-raised as
+`OrxError` / `OrxValueError` on the client, so `api.py:125-127`'s "log and return no documents"
+behaviour is unchanged.
+"""
+from __future__ import annotations
+
+import asyncio
+import os
+import socket
+import struct
+import threading
+from typing import Optional
+
+import msgpack
+import numpy as np
+
+from ._lib import ORX_ERR_INVALID, OrxError, OrxValueError
+from .batcher import QueryBatcher
+
+
+def _pack_arr(a: np.ndarray) -> dict:
+    a = np.ascontiguousarray(a)
+    return {"shape": list(a.shape), "dtype": a.dtype.str, "data": a.tobytes()}
+
+
+def _unpack_arr(d: dict) -> np.ndarray:
+    return np.frombuffer(d["data"], dtype=np.dtype(d["dtype"])).reshape(d["shape"]).copy()
+
+
+def _err_payload(e: Exception) -> dict:
+    code = getattr(e, "code", -100)
+    return {"err": int(code), "msg": getattr(e, "message", str(e)), "value_error": isinstance(e, ValueError)}
+
+
+def _raise_from(resp: dict):
+    cls = OrxValueError if resp.get("value_error") else OrxError
+    raise cls(resp["err"], resp["msg"])
+
+
+# --------------------------------------------------------------------------------- server
+class IndexServer:
+    """Owns `index`; serve with `await server.start()` / `await server.serve_forever()`."""
+
+    def __init__(self, index, path: str, batch_window_ms: Optional[float] = 1.0, max_batch: int = 256):
+        self.index = index
+        self.path = path
+        self.batcher = QueryBatcher(index, max_batch, batch_window_ms) if batch_window_ms is not None else None
+        self._server: Optional[asyncio.AbstractServer] = None
+        self._write_lock = asyncio.Lock()
+
+    async def start(self) -> None:
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+        self._server = await asyncio.start_unix_server(self._client, path=self.path)
+
+    async def serve_forever(self) -> None:
+        async with self._server:
+            await self._server.serve_forever()
+
+    async def close(self) -> None:
+        if self.batcher is not None:
+            await self.batcher.drain()
+        if self._server is not None:
+            self._server.close()
+            await self._server.wait_closed()
+        if os.path.exists(self.path):
+            os.unlink(self.path)
+
+    async def _client(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter) -> None:
+        try:
+            while True:
+                head = await reader.readexactly(4)
+                body = await reader.readexactly(struct.unpack(">I", head)[0])
+                req = msgpack.unpackb(body, raw=False)
+                # requests of one connection are answered in order; different connections interleave
+                resp = await self._handle(req)
+                out = msgpack.packb(resp, use_bin_type=True)
+                writer.write(struct.pack(">I", len(out)) + out)
+                await writer.drain()
+        except (asyncio.IncompleteReadError, ConnectionResetError, BrokenPipeError):
+            pass
+        finally:
+            writer.close()
+
+    async def _handle(self, req: dict) -> dict:
+        try:
+            op = req.get("op")
+            if op == "search":
+                Q = _unpack_arr(req["q"])
+                k = int(req["k"])
+                if self.batcher is not None:
+                    res = await asyncio.gather(*[self.batcher.search(q, k) for q in Q], return_exceptions=True)
+                    for r in res:
+                        if isinstance(r, Exception):
+                            raise r
+                    ids = np.zeros((len(res), k, 2), np.uint64)
+                    dist = np.full((len(res), k), np.nan)
+                    cnt = np.zeros(len(res), np.int32)
+                    for i, (a, b) in enumerate(res):
+                        ids[i, :len(b)], dist[i, :len(b)], cnt[i] = a, b, len(b)
+                else:
+                    ids, dist, cnt = await asyncio.to_thread(self.index.search, Q, k)
+                return {"ids": _pack_arr(ids), "dist": _pack_arr(dist), "cnt": _pack_arr(cnt)}
+            if op == "upsert":
+                async with self._write_lock:
+                    await asyncio.to_thread(self.index.upsert, _unpack_arr(req["ids"]), _unpack_arr(req["vecs"]))
+                return {"ok": True}
+            if op == "delete":
+                async with self._write_lock:
+                    n = await asyncio.to_thread(self.index.delete, _unpack_arr(req["ids"]))
+                return {"removed": int(n)}
+            if op == "size":
+                return {"size": len(self.index)}
+            return {"err": ORX_ERR_INVALID, "msg": f"unknown op {op!r}", "value_error": True}
+        except Exception as e:      # noqa: BLE001 -- every failure travels back to the caller
+            return _err_payload(e)
+
+
+def serve_in_thread(index, path: str, **kw) -> "ServerThread":
+    """Run an `IndexServer` on its own event loop in a daemon thread (tests, single-binary deployments)."""
+    t = ServerThread(index, path, **kw)
+    t.start()
+    t.ready.wait(10)
+    return t
+
+
+class ServerThread(threading.Thread):
+    def __init__(self, index, path: str, **kw):
+        super().__init__(daemon=True)
+        self.index, self.path, self.kw = index, path, kw
+        self.ready = threading.Event()
+        self.loop: Optional[asyncio.AbstractEventLoop] = None
+        self.server: Optional[IndexServer] = None
+
+    def run(self) -> None:
+        self.loop = asyncio.new_event_loop()
+        asyncio.set_event_loop(self.loop)
+        self.server = IndexServer(self.index, self.path, **self.kw)
+        self.loop.run_until_complete(self.server.start())
+        self.ready.set()
+        try:
+            self.loop.run_forever()
+        finally:
+            self.loop.run_until_complete(self.server.close())
+            self.loop.close()
+
+    def stop(self) -> None:
+        if self.loop is not None:
+            self.loop.call_soon_threadsafe(self.loop.stop)
+        self.join(10)
+
+
+# --------------------------------------------------------------------------------- client
+class RemoteIndex:
+    """`Index`-shaped proxy used by a worker process: blocking calls over one unix socket
+    (thread-safe; `GpuVectorStore` already runs index calls in `asyncio.to_thread`)."""
+
+    def __init__(self, path: str, timeout: float = 60.0):
+        self.path = path
+        self._sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self._sock.settimeout(timeout)
+        self._sock.connect(path)
+        self._lock = threading.Lock()
+
+    def close(self) -> None:
+        try:
+            self._sock.close()
+        except OSError:
+            pass
+
+    def _call(self, req: dict) -> dict:
+        out = msgpack.packb(req, use_bin_type=True)
+        with self._lock:
+            self._sock.sendall(struct.pack(">I", len(out)) + out)
+            head = self._recv(4)
+            resp = msgpack.unpackb(self._recv(struct.unpack(">I", head)[0]), raw=False)
+        if "err" in resp:
+            _raise_from(resp)
+        return resp
+
+    def _recv(self, n: int) -> bytes:
+        buf = bytearray()
+        while len(buf) < n:
+            chunk = self._sock.recv(n - len(buf))
+            if not chunk:
+                raise OrxError(-100, "index server closed the connection")
+            buf += chunk
+        return bytes(buf)
+
+    def __len__(self) -> int:
+        return int(self._call({"op": "size"})["size"])
+
+    def search(self, queries, k: int = 12):
+        q = np.asarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        r = self._call({"op": "search", "q": _pack_arr(q), "k": int(k)})
+        return _unpack_arr(r["ids"]), _unpack_arr(r["dist"]), _unpack_arr(r["cnt"])
+
+    def upsert(self, ids, vecs) -> None:
+        from .engine import ids_to_array
+        self._call({"op": "upsert", "ids": _pack_arr(ids_to_array(ids)), "vecs": _pack_arr(np.asarray(vecs, np.float32))})
+
+    def delete(self, ids) -> int:
+        from .engine import ids_to_array
+        return int(self._call({"op": "delete", "ids": _pack_arr(ids_to_array(ids))})["removed"])
+
+
+__all__ = ["IndexServer", "RemoteIndex", "ServerThread", "serve_in_thread"]

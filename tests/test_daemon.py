@@ -1,0 +1,113 @@
+"""`IndexServer` / `RemoteIndex`: one table owner, several worker processes (reference
+app/entrypoint.sh:16 starts 2 uvicorn workers).  CPU: protocol, ordering, error transport and
+cross-connection batching with an oracle-backed fake; GPU: a real index served to a child process."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from oracle import cosine_topk as O
+from tests.test_batcher import FakeIndex
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class FakeOwner(FakeIndex):
+    def __init__(self, X, ids):
+        super().__init__(X.copy(), ids.copy())
+        self.log = []
+
+    def __len__(self):
+        return self.ids.shape[0]
+
+    def upsert(self, ids, vecs):
+        self.log.append(("upsert", len(ids)))
+        self.ids = np.concatenate([self.ids, np.asarray(ids, np.uint64).reshape(-1, 2)])
+        self.X = np.concatenate([self.X, np.asarray(vecs, np.float32)])
+
+    def delete(self, ids):
+        kill = {tuple(map(int, r)) for r in np.asarray(ids, np.uint64).reshape(-1, 2)}
+        keep = np.array([tuple(map(int, r)) not in kill for r in self.ids], bool)
+        self.log.append(("delete", int((~keep).sum())))
+        self.ids, self.X = self.ids[keep], self.X[keep]
+        return int((~keep).sum())
+
+
+def test_two_workers_share_one_owner(small_table, tmp_path):
+    import outline_rag_b200 as orx
+    from outline_rag_b200.daemon import RemoteIndex, serve_in_thread
+    X, Q, _ = small_table
+    owner = FakeOwner(X[:500], O.ids_arange(0, 500))
+    path = str(tmp_path / "orx.sock")
+    srv = serve_in_thread(owner, path, batch_window_ms=30.0, max_batch=64)
+    try:
+        a, b = RemoteIndex(path), RemoteIndex(path)
+        assert len(a) == 500
+        results = {}
+
+        def worker(name, client, qs):
+            results[name] = [client.search(Q[i], 12) for i in qs]
+
+        t1 = threading.Thread(target=worker, args=("a", a, [0, 1, 2]))
+        t2 = threading.Thread(target=worker, args=("b", b, [3, 4, 5]))
+        t1.start(); t2.start(); t1.join(); t2.join()
+        for name, qs in (("a", [0, 1, 2]), ("b", [3, 4, 5])):
+            for (ids, dist, cnt), qi in zip(results[name], qs):
+                w_ids, w_d = O.topk_exact(X[:500], O.ids_arange(0, 500), Q[qi], 12)
+                assert cnt[0] == 12 and np.array_equal(ids[0], w_ids) and np.array_equal(dist[0], w_d)
+        assert max(n for n, _ in owner.calls) >= 2            # requests of the two workers shared a scan
+        # writes pass through in order; a search acknowledged after them sees them
+        a.upsert(O.ids_arange(900, 903), X[600:603])
+        assert b.delete(O.ids_arange(0, 2)) == 2 and len(b) == 501
+        got = b.search(X[601], 1)
+        assert O.ids_to_ints(got[0][0]) == [901]
+        assert owner.log == [("upsert", 3), ("delete", 2)]
+        with pytest.raises(orx.OrxValueError, match="dimensions"):
+            a.search(np.zeros((1, 100), np.float32), 12)
+        with pytest.raises(orx.OrxValueError):
+            a.search(Q[0], 1000)
+        ok = a.search(Q[0], 3)                                  # the connection survives an error reply
+        assert ok[2][0] == 3
+        a.close(); b.close()
+    finally:
+        srv.stop()
+    assert not os.path.exists(path)
+
+
+CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1])
+from outline_rag_b200.daemon import RemoteIndex
+from outline_rag_b200.synth import Synth
+syn = Synth(1024)
+Q, _ = syn.queries(4, 8192)
+ix = RemoteIndex(sys.argv[2])
+ids, dist, cnt = ix.search(Q, 12)
+print(len(ix), ids[:, :, 1].tolist(), [float(d).hex() for d in dist[0]])
+"""
+
+
+@pytest.mark.gpu
+def test_real_index_served_to_another_process(small_table, tmp_path):
+    import outline_rag_b200 as orx
+    from outline_rag_b200.daemon import serve_in_thread
+    X, Q, _ = small_table
+    ids = O.ids_arange(0, X.shape[0])
+    path = str(tmp_path / "orx.sock")
+    with orx.Index("fp32") as ix:
+        ix.upsert(ids, X)
+        srv = serve_in_thread(ix, path, batch_window_ms=2.0)
+        try:
+            out = subprocess.run([sys.executable, "-c", CHILD, ROOT, path], capture_output=True, text=True, timeout=120)
+            assert out.returncode == 0, out.stderr[-1500:]
+            size, got_ids, dist0 = eval(out.stdout.strip().splitlines()[-1])
+        finally:
+            srv.stop()
+    assert size == X.shape[0]
+    for i in range(4):
+        w_ids, w_d = O.topk_exact(X, ids, Q[i], 12)
+        assert got_ids[i] == O.ids_to_ints(w_ids)
+    assert dist0 == [float(d).hex() for d in O.topk_exact(X, ids, Q[0], 12)[1]]
