@@ -1,6 +1,7 @@
 """`IndexServer` / `RemoteIndex`: one table owner, several worker processes (reference
 app/entrypoint.sh:16 starts 2 uvicorn workers).  CPU: protocol, ordering, error transport and
 cross-connection batching with an oracle-backed fake; GPU: a real index served to a child process."""
+import json
 import os
 import subprocess
 import sys
@@ -78,7 +79,7 @@ def test_two_workers_share_one_owner(small_table, tmp_path):
 
 
 CHILD = r"""
-import sys, numpy as np
+import json, sys, numpy as np
 sys.path.insert(0, sys.argv[1])
 from outline_rag_b200.daemon import RemoteIndex
 from outline_rag_b200.synth import Synth
@@ -86,7 +87,7 @@ syn = Synth(1024)
 Q, _ = syn.queries(4, 8192)
 ix = RemoteIndex(sys.argv[2])
 ids, dist, cnt = ix.search(Q, 12)
-print(len(ix), ids[:, :, 1].tolist(), [float(d).hex() for d in dist[0]])
+print(json.dumps([len(ix), ids[:, :, 1].tolist(), [float(d).hex() for d in dist[0]]]))
 """
 
 
@@ -103,7 +104,7 @@ def test_real_index_served_to_another_process(small_table, tmp_path):
         try:
             out = subprocess.run([sys.executable, "-c", CHILD, ROOT, path], capture_output=True, text=True, timeout=120)
             assert out.returncode == 0, out.stderr[-1500:]
-            size, got_ids, dist0 = eval(out.stdout.strip().splitlines()[-1])
+            size, got_ids, dist0 = json.loads(out.stdout.strip().splitlines()[-1])
         finally:
             srv.stop()
     assert size == X.shape[0]
