@@ -1,0 +1,114 @@
+"""Host-side logic that needs no GPU: id conversions, the shard function, the doc-store filter
+grammar, and `GpuVectorStore`'s call sequence against an oracle-backed fake index."""
+import asyncio
+import uuid
+
+import numpy as np
+import pytest
+
+from oracle import cosine_topk as O
+from tests.test_daemon import FakeOwner
+
+
+def test_id_conversions_roundtrip_and_uuid_order():
+    from outline_rag_b200.engine import ids_to_array, ids_to_ints, ids_to_uuid_strs
+    vals = [0, 1, 2**64 - 1, 2**64, (1 << 127) | 5, 2**128 - 1]
+    a = ids_to_array(vals)
+    assert a.dtype == np.uint64 and a.shape == (6, 2) and ids_to_ints(a) == vals
+    strs = ids_to_uuid_strs(a)
+    assert strs[1] == "00000000-0000-0000-0000-000000000001" and ids_to_ints(ids_to_array(strs)) == vals
+    assert ids_to_ints(ids_to_array([uuid.UUID(int=7)])) == [7]
+    assert ids_to_ints(ids_to_array(np.array([3, 9], np.int64))) == [3, 9]
+    # (hi, lo) lexicographic order == integer order == Postgres uuid byte order
+    order = sorted(range(6), key=lambda i: (int(a[i, 0]), int(a[i, 1])))
+    assert order == sorted(range(6), key=lambda i: vals[i])
+    with pytest.raises(ValueError):
+        ids_to_array([2**128])
+    with pytest.raises(ValueError):
+        ids_to_array(["not-a-uuid"])
+
+
+def test_shard_function_is_balanced_and_stable():
+    from outline_rag_b200.sharded import shard_of
+    ids = O.ids_arange(0, 200_000)
+    for world in (2, 4, 8):
+        s = shard_of(ids, world)
+        counts = np.bincount(s, minlength=world)
+        assert counts.min() > 0.97 * 200_000 / world and counts.max() < 1.03 * 200_000 / world
+        assert np.array_equal(s[:1000], shard_of(ids[:1000], world))        # depends on the id only
+    wide = O.ids_from_ints([(i << 64) | 17 for i in range(4000)])            # only the high word varies
+    assert np.bincount(shard_of(wide, 8), minlength=8).min() > 400
+
+
+def test_doc_store_filter_grammar():
+    from outline_rag_b200.vectorstore import MemoryDocStore
+    st = MemoryDocStore()
+    st.put_many(["a", "b", "c", "d"], ["t"] * 4,
+                [{"source_id": "d1", "title": "x"}, {"source_id": "d1", "title": "y"},
+                 {"source_id": "d2", "title": "x"}, {"source_id": "d3", "title": "z"}])
+    assert st.ids_for_filter({"source_id": "d1"}) == ["a", "b"]
+    assert st.ids_for_filter({"source_id": {"$in": ["d2", "d3"]}}) == ["c", "d"]
+    assert st.ids_for_filter({"$and": [{"source_id": "d1"}, {"title": {"$eq": "y"}}]}) == ["b"]
+    assert st.ids_for_filter({"$or": [{"title": "z"}, {"title": {"$ne": "x"}, "source_id": "d1"}]}) == ["b", "d"]
+    assert st.ids_for_filter({"source_id": "nope"}) == []
+    assert st.ids_for_source(["d1", "d3"]) == ["a", "b", "d"]
+    with pytest.raises(NotImplementedError):
+        st.ids_for_filter({"title": {"$like": "x%"}})
+
+
+class FakeStoreIndex(FakeOwner):
+    """Index stand-in that accepts whatever id forms `GpuVectorStore` passes (uuid strings)."""
+
+    def upsert(self, ids, vecs):
+        from outline_rag_b200.engine import ids_to_array
+        super().upsert(ids_to_array(ids), vecs)
+
+    def delete(self, ids):
+        from outline_rag_b200.engine import ids_to_array
+        return super().delete(ids_to_array(ids))
+
+    def search_filtered(self, q, k, allow):
+        from outline_rag_b200.engine import ids_to_array
+        ok = {tuple(r) for r in ids_to_array(allow).tolist()}
+        keep = np.array([tuple(r) in ok for r in self.ids.tolist()], bool)
+        return FakeOwner(self.X[keep], self.ids[keep]).search(np.asarray(q, np.float32).reshape(1, -1), k)
+
+
+class FakeEmb:
+    def __init__(self, X):
+        self.X = X
+
+    async def aembed_documents(self, texts):
+        return [self.X[int(t)] for t in texts]
+
+    async def aembed_query(self, text):
+        return self.X[int(text)]
+
+
+def test_vectorstore_call_sequence_on_a_fake_index(small_table):
+    """rag.py's order: look up the old chunk ids of the refreshed docs, adelete them, aadd_documents the
+    re-chunked ones; ids default to uuid4; hits are hydrated in rank order; batching is transparent."""
+    import outline_rag_b200 as orx
+    X, _, _ = small_table
+    owner = FakeStoreIndex(np.zeros((0, 1024), np.float32), np.zeros((0, 2), np.uint64))
+    store = orx.GpuVectorStore(owner, FakeEmb(X), batch_window_ms=5.0)
+
+    async def run():
+        docs = [orx.Document(page_content=str(i), metadata={"source_id": f"d{i // 10}"}, id=str(uuid.UUID(int=i)))
+                for i in range(100)]
+        assert await store.aadd_documents(docs) == [d.id for d in docs]
+        more = await store.aadd_documents([orx.Document(page_content="150", metadata={"source_id": "dx"})])
+        assert len(more) == 1 and uuid.UUID(more[0]).version == 4
+        hits = await asyncio.gather(*[store.as_retriever(search_kwargs={"k": 5}).ainvoke(str(i)) for i in (3, 42, 77)])
+        assert [h[0].page_content for h in hits] == ["3", "42", "77"] and all(len(h) == 5 for h in hits)
+        assert store.batcher.batches == 1                                    # three requests, one scan
+        stale = store.doc_store.ids_for_source(["d4"])
+        assert await store.adelete(ids=stale) is True and len(owner) == 91
+        assert "42" not in [h.page_content for h in await store.asimilarity_search("42", k=12)]
+        only_d7 = await asyncio.to_thread(store.similarity_search_with_score_by_vector, X[3], 12, {"source_id": "d7"})
+        assert sorted(int(d.page_content) for d, _ in only_d7) == list(range(70, 80))
+        assert [s for _, s in only_d7] == sorted(s for _, s in only_d7)
+        await store.batcher.drain()
+
+    asyncio.run(run())
+    assert [op for op, _ in owner.log] == ["upsert", "upsert", "delete"]
