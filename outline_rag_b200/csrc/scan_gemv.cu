@@ -21,13 +21,14 @@
 
 namespace orx {
 
-constexpr int ROWS_PER_ITER = 2;
+template <typename T> struct RowsPerIter { static constexpr int value = sizeof(T) == 4 ? 2 : 4; };   // 8 KB per warp in flight
 
 template <typename T, int S>
 __global__ void __launch_bounds__(SCAN_THREADS, 2)
 scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, uint32_t n_rows,
                  const float *__restrict__ qhat_all, uint64_t *__restrict__ partial_all) {
     constexpr int NV = RowVec<T>::NV;
+    constexpr int ROWS_PER_ITER = RowsPerIter<T>::value;
     constexpr int K = 32 * S;
     __shared__ uint64_t s_keys[SCAN_WARPS][K];
 
@@ -92,6 +93,7 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
 int scan_gemv_grid(int device, uint32_t n_rows) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    constexpr int ROWS_PER_ITER = 2;      // grid sizing only: enough chunks for every warp of the persistent grid
     uint32_t chunks = (n_rows + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
     uint32_t want = (chunks + SCAN_WARPS - 1) / SCAN_WARPS;
     uint32_t full = (uint32_t)sms * 2u;
