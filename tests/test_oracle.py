@@ -181,3 +181,41 @@ def test_golden_vectors(synth100k):
         got_ids, got_d = O.topk_exact(X, ids, Q[qi], G["k"])
         assert O.ids_to_ints(got_ids) == case["ids"]
         assert [float(d).hex() for d in got_d] == case["dist_hex"]
+
+
+# ---------------------------------------------------------------- properties (hypothesis, CPU)
+from hypothesis import given, settings            # noqa: E402
+from hypothesis import strategies as st           # noqa: E402
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(0, 2**31 - 1), st.integers(1, 60), st.integers(1, 5), st.integers(1, 20))
+def test_merging_any_partition_equals_the_global_answer(seed, n, parts, k):
+    """ORDER BY ... LIMIT k over a union of disjoint shards == merge of the per-shard answers, for any
+    partition (the invariant the row-sharded path relies on), including duplicates and zero rows."""
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((max(1, n // 3), DIM)).astype(np.float32)
+    X = base[rng.integers(0, base.shape[0], size=n)]                 # many exact duplicates
+    X[rng.random(n) < 0.1] = 0.0                                     # some zero-norm rows
+    ids = O.ids_from_ints(rng.choice(10 * n + 10, size=n, replace=False).tolist())
+    q = rng.standard_normal(DIM).astype(np.float32)
+    owner = rng.integers(0, parts, size=n)
+    shard_answers = [O.topk_exact(X[owner == p], ids[owner == p], q, k, exhaustive=True) for p in range(parts)]
+    m_ids, m_d = O.merge_shards(shard_answers, k)
+    g_ids, g_d = O.topk_exact(X, ids, q, k, exhaustive=True)
+    assert np.array_equal(m_ids, g_ids)
+    assert np.array_equal(np.isnan(m_d), np.isnan(g_d)) and np.array_equal(m_d[~np.isnan(m_d)], g_d[~np.isnan(g_d)])
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(0, 2**31 - 1))
+def test_canonical_distance_is_within_an_ulp_of_exact_arithmetic(seed):
+    import math
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal(DIM).astype(np.float32)
+    q = rng.standard_normal(DIM).astype(np.float32)
+    d = O.canon_distance(x[None, :], q)[0]
+    xd, qd = x.astype(np.float64), q.astype(np.float64)
+    exact = 1.0 - math.fsum(xd * qd) / math.sqrt(math.fsum(xd * xd) * math.fsum(qd * qd))
+    assert abs(d - exact) <= 1e-14
+    assert O.canon_distance(x[None, :] * np.float32(4.0), q * np.float32(0.5))[0] == d      # scale-free, exactly
