@@ -156,6 +156,33 @@ int orx_fetch(orx_index *idx, const orx_id *ids, uint64_t n, float *out_vecs, in
 int orx_export_rows(orx_index *idx, uint64_t row_start, uint64_t n, orx_id *ids_out, void *rows_out);
 int orx_import_rows(orx_index *idx, const orx_id *ids, const void *rows_raw, uint64_t n);
 
+/* ---- pgvector wire formats on either side of the path ------------------
+ * Cold start: the device table is rebuilt from
+ *   COPY (SELECT langchain_id, embedding FROM langchain_pg_embedding) TO STDOUT (FORMAT binary)
+ * (table: reference app/database.py:118-131; the reference's driver, psycopg 3 -- requirements.txt:5 --
+ * yields that stream chunk by chunk from `cursor.copy(...)`).  orx_pgcopy_feed accepts the stream in
+ * chunks of ANY size; complete tuples are staged in pinned memory, decoded on the GPU (big-endian float4
+ * image of pgvector's vector_send [UPSTREAM src/vector.c]) and upserted 16384 rows at a time.  Checks
+ * and messages follow Postgres' CopyFrom and pgvector's vector_recv: signature / flags, 2 columns,
+ * 16-byte uuid, dim == 1024 (ORX_ERR_DIM), unused == 0, NaN / infinite element (ORX_ERR_NONFINITE; the
+ * batch holding it is rejected).  Rows whose embedding is NULL (the column is nullable) are skipped and
+ * counted.  An id seen before -- in the table or earlier in the stream -- is replaced (upsert).
+ * After an error every later feed fails; batches flushed before it stay loaded.  orx_pgcopy_close flushes
+ * the tail, reports the totals and frees the loader, also after an error (its return code repeats it).
+ * idx == NULL opens a DRY RUN: framing and element checks on the host, nothing loaded, no GPU needed. */
+typedef struct orx_pgcopy orx_pgcopy;
+int orx_pgcopy_open(orx_index *idx, orx_pgcopy **out);
+int orx_pgcopy_feed(orx_pgcopy *ld, const void *bytes, uint64_t n);
+int orx_pgcopy_close(orx_pgcopy *ld, uint64_t *rows_loaded, uint64_t *rows_null);
+
+/* pgvector's text input `vector_in` [UPSTREAM src/vector.c]: '[0.1, 0.2, ...]' -> fp32.  This is the
+ * format the reference sends the query vector (:q of the SQL above) and the stored embeddings in
+ * (langchain-postgres formats the Python float list with str(); pgvector parses each element with strtof,
+ * i.e. ONE rounding decimal -> fp32).  text need not be NUL-terminated; out [dim]; the vector must have
+ * exactly dim elements.  Host-only (no GPU).  Errors as pgvector: syntax / out of range -> ORX_ERR_INVALID,
+ * dimension -> ORX_ERR_DIM, NaN / infinity -> ORX_ERR_NONFINITE. */
+int orx_parse_vector_text(const char *text, uint64_t len, float *out, int dim);
+
 /* Synthetic bge-m3-shaped table generator, bit-identical to
  * outline_rag_b200/synth.py.  Fills dst_device [n_rows, 1024] fp32 with rows
  * row_start .. row_start+n_rows-1.  centres/mean are built on first use. */

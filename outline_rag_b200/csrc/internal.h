@@ -75,6 +75,16 @@ void launch_move_rows(int dtype, const uint32_t *src_row, const uint32_t *dst_ro
 void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint32_t n, float *out,
                         cudaStream_t st);
 
+// ---- pgwire.cu (pgvector wire formats: COPY BINARY bulk load, text input)
+void launch_decode_pgvector(const uint8_t *raw, const uint64_t *payload_off, uint32_t n, float *out,
+                            cudaStream_t st);
+
+// ---- orx_api.cu: what the other translation units need from an index
+int set_error(int code, const char *fmt, ...);     // records the thread-local message, returns code
+cudaStream_t index_stream(const orx_index *ix);
+int index_device(const orx_index *ix);
+void index_count_launches(orx_index *ix, uint64_t n);
+
 // ---- synth.cu
 void launch_synth_unit(uint64_t key, uint32_t n_vec, float *dst, cudaStream_t st);
 void launch_synth_rows(uint64_t key_noise, uint64_t key_cid, const float *mean, const float *centres,

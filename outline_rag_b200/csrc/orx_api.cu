@@ -619,6 +619,27 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
 
 }  // namespace
 
+namespace orx {
+int set_error(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+cudaStream_t index_stream(const orx_index *ix) {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    return ix->stream;
+}
+int index_device(const orx_index *ix) { return ix->device; }
+void index_count_launches(orx_index *ix, uint64_t n) {
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->stats.kernel_launches += n;
+}
+}  // namespace orx
+
 // =============================================================================== C-ABI
 extern "C" {
 

@@ -79,6 +79,69 @@ def _host_f32(x, what: str) -> np.ndarray:
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def parse_vector_text(text, dim: int = ORX_DIM) -> np.ndarray:
+    """pgvector's text input (``'[0.1, 0.2, ...]'`` -> fp32 ``[dim]``) with its checks: the format the
+    reference sends the query vector and the stored embeddings in.  One rounding, decimal -> fp32
+    (``np.asarray(list_of_python_floats, float32)`` rounds twice; the two differ only when the double
+    sits on an fp32 rounding boundary).  Host-only; raises OrxValueError like pgvector raises."""
+    raw = text.encode("ascii", "replace") if isinstance(text, str) else bytes(text)
+    out = np.empty(int(dim), np.float32)
+    check(lib.orx_parse_vector_text(raw, len(raw), C.c_void_p(out.ctypes.data), int(dim)))
+    return out
+
+
+class PgCopyLoader:
+    """Streaming cold-start load from ``COPY (SELECT langchain_id, embedding FROM langchain_pg_embedding)
+    TO STDOUT (FORMAT binary)`` (`orx_pgcopy_*`; table: reference app/database.py:118-131).
+
+    ``feed`` takes the stream in chunks of any size (bytes / bytearray / memoryview, e.g. what psycopg 3's
+    ``async for data in copy`` yields); ``close`` flushes and returns ``(rows_loaded, rows_null)``.
+    ``index=None`` is a dry run that only validates the stream on the host (no GPU)."""
+
+    def __init__(self, index: "Index | None" = None):
+        self._ld = C.c_void_p()
+        self._index = index          # keeps the table alive while the loader holds its handle
+        self.result = None           # (rows_loaded, rows_null) once closed
+        check(lib.orx_pgcopy_open(index._h if index is not None else None, C.byref(self._ld)))
+
+    def feed(self, data) -> None:
+        if not self._ld:
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "loader is closed")
+        a = np.frombuffer(data, dtype=np.uint8)          # zero-copy view of any contiguous buffer
+        if a.size:
+            check(lib.orx_pgcopy_feed(self._ld, C.c_void_p(a.ctypes.data), a.size))
+
+    def close(self) -> tuple[int, int]:
+        if not self._ld:
+            return (0, 0)
+        rows, nulls = C.c_uint64(0), C.c_uint64(0)
+        ld, self._ld = self._ld, C.c_void_p()
+        rc = lib.orx_pgcopy_close(ld, C.byref(rows), C.byref(nulls))
+        self.result = (int(rows.value), int(nulls.value))
+        check(rc)
+        return self.result
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, exc_type, *exc):
+        if exc_type is None:
+            self.close()
+        else:                         # already failing: free the loader, keep the original exception
+            try:
+                self.close()
+            except OrxError:
+                pass
+
+    def __del__(self):
+        try:
+            if self._ld:
+                lib.orx_pgcopy_close(self._ld, None, None)
+                self._ld = C.c_void_p()
+        except Exception:
+            pass
+
+
 class Index:
     """One GPU's share of ``langchain_pg_embedding.embedding`` (reference app/database.py:118-131).
 
@@ -227,6 +290,20 @@ class Index:
                                          int(stride_bytes), C.c_void_p(ids_out.data_ptr()),
                                          C.c_void_p(dist_out.data_ptr()), C.c_void_p(counts_out.data_ptr())))
 
+    # -- cold start from Postgres
+    def pgcopy_loader(self) -> PgCopyLoader:
+        return PgCopyLoader(self)
+
+    def load_pgcopy(self, chunks) -> tuple[int, int]:
+        """Feed an iterable of COPY BINARY chunks (or one bytes object); -> (rows_loaded, rows_null)."""
+        if isinstance(chunks, (bytes, bytearray, memoryview)):
+            chunks = (chunks,)
+        ld = PgCopyLoader(self)
+        with ld:
+            for c in chunks:
+                ld.feed(c)
+        return ld.result
+
     # -- snapshot / cold start (SURVEY.md 8f-2)
     SNAPSHOT_CHUNK = 65536
 
@@ -347,4 +424,4 @@ def synth_rows_device(device: int, seed: int, n_centres: int, row_start: int, n_
     return out
 
 
-__all__ = ["Index", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device"]
+__all__ = ["Index", "PgCopyLoader", "parse_vector_text", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device"]

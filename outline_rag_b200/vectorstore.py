@@ -208,6 +208,37 @@ class GpuVectorStore:
     async def adelete(self, ids: Optional[Sequence] = None, **kw: Any) -> bool:
         return await asyncio.to_thread(self.delete, ids, **kw)
 
+    # ---------------------------------------------------------------- cold start
+    COPY_SQL = ("COPY (SELECT langchain_id, embedding FROM {table} WHERE embedding IS NOT NULL) "
+                "TO STDOUT (FORMAT binary)")
+
+    def load_pgcopy(self, chunks) -> tuple[int, int]:
+        """Rebuild the device table from a COPY BINARY stream of ``(langchain_id, embedding)``
+        (`COPY_SQL`); content and metadata stay where they are (Postgres).  -> (rows_loaded, rows_null)."""
+        return self.index.load_pgcopy(chunks)
+
+    async def aload_pgcopy(self, chunks, feed_bytes: int = 8 << 20) -> tuple[int, int]:
+        """Same, for an async iterator such as psycopg 3's ``async with cur.copy(sql) as copy: async for
+        data in copy``.  Driver chunks are small (tens of KB); they are coalesced to `feed_bytes` so the
+        event loop pays one thread hop per 8 MB, not per chunk."""
+        ld = self.index.pgcopy_loader()
+        pending = bytearray()
+        try:
+            async for data in chunks:
+                pending += data
+                if len(pending) >= feed_bytes:
+                    block, pending = pending, bytearray()
+                    await asyncio.to_thread(ld.feed, block)
+            if pending:
+                await asyncio.to_thread(ld.feed, pending)
+        except BaseException:
+            try:
+                ld.close()
+            except Exception:
+                pass
+            raise
+        return await asyncio.to_thread(ld.close)
+
     # ---------------------------------------------------------------- reads
     def _hydrate(self, ids_row: np.ndarray, dist_row: np.ndarray, count: int) -> list[tuple[Any, float]]:
         sids = ids_to_uuid_strs(ids_row[:count])
