@@ -106,9 +106,11 @@ int orx_search(orx_index *idx, const float *queries, int nq, int dim, int k,
 /* The same query restricted to a set of chunk ids -- the SQL with a WHERE clause, i.e. what the
  * upstream store's `filter=` argument compiles to after the metadata predicate has been resolved to
  * `langchain_id`s (e.g. `source_id = ANY(...)`, reference app/rag.py:216-224 shows that look-up).
- * allow_ids [n_allow] host; unknown ids are ignored, duplicates count once.  Every eligible row is
- * rescored canonically (no coarse pass), so the result is exact by construction; cost is
- * O(n_allow) row reads per query.  Same outputs and ordering as orx_search. */
+ * allow_ids [n_allow] host; unknown ids are ignored, duplicates count once.  Up to 4095 eligible rows
+ * are each rescored canonically (no scan; O(n_allow) row reads per query).  From 4096 eligible rows on
+ * the predicate becomes a row bitmap and the sequential scan skips the rows whose bit is clear (HBM
+ * traffic = eligible rows only), with the same candidate proof as orx_search; an unproven query falls
+ * back to the rescoring path.  Exact either way.  Same outputs and ordering as orx_search. */
 int orx_search_filtered(orx_index *idx, const float *queries, int nq, int dim, int k,
                         const orx_id *allow_ids, uint64_t n_allow,
                         orx_id *out_ids, double *out_dist, int *out_counts);

@@ -63,6 +63,11 @@ void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t
                       const float *qhat, int nq, int slots, uint64_t *partial, int grid,
                       cudaStream_t st);
 
+// the same scan over the rows whose bit is set in allow_bits [(n_rows+31)/32 words; bits >= n_rows are 0]
+void launch_scan_gemv_filtered(int dtype, const void *table, const float *scale, uint32_t n_rows,
+                               const uint32_t *allow_bits, const float *qhat, int nq, int slots,
+                               uint64_t *partial, int grid, cudaStream_t st);
+
 // ---- table_ops.cu
 void launch_validate_rows(const float *src, uint64_t n, int *flag, cudaStream_t st);
 void launch_commit_rows(int dtype, const float *src, const uint32_t *src_idx, const uint32_t *dst_row,

@@ -169,6 +169,9 @@ struct orx_index {
     PinBuf<double> h_dist;
     PinBuf<int> h_counts, h_flags, h_myflags, h_redo;
     struct Exchange *xchg = nullptr;     // peer-memory exchange of the row-sharded search (orx_shard_*)
+    // filtered search: eligibility bitmap (one bit per row) for the filtered scan
+    DevBuf<uint32_t> allow_bits;
+    PinBuf<uint32_t> h_allow_bits;
     // exhaustive fallback scratch
     DevBuf<uint32_t> fb_list, fb_count;
     DevBuf<double> fb_dist;
@@ -335,6 +338,7 @@ int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const Se
     return ORX_OK;
 }
 
+constexpr uint32_t FILTER_SCAN_MIN_ROWS = 4096;   // eligible rows from which the bitmap scan replaces rescoring them all
 constexpr int ZERO_COPY_MAX_Q = 16;     // query batches up to this size are read by the prep kernel over PCIe
 
 // ---- query staging: *q_src is what the rescoring kernels read (device memory); launches prep
@@ -697,6 +701,7 @@ void orx_destroy(orx_index *ix) {
     ix->h_q.release(); ix->h_prep.release(); ix->h_ids.release(); ix->h_dist.release();
     ix->h_counts.release(); ix->h_flags.release();
     ix->fb_list.release(); ix->fb_count.release(); ix->fb_dist.release();
+    ix->allow_bits.release(); ix->h_allow_bits.release();
     ix->stage.release(); ix->d_src_idx.release(); ix->d_dst_row.release(); ix->d_ids.release();
     ix->d_flag.release(); ix->h_u32a.release(); ix->h_u32b.release(); ix->h_flag.release();
     for (auto &e : ix->scan_ev) cudaEventDestroy(e);
@@ -959,14 +964,57 @@ int orx_search_filtered(orx_index *ix, const float *queries, int nq, int dim, in
     CK(ix->fb_count.ensure(1));
     if (m) CK(cudaMemcpyAsync(ix->fb_list.p, rows.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ix->fb_count.p, &m, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    // few rows: no scan at all -- every eligible row is rescored canonically and the k best are selected
-    for (int j = 0; j < nq; ++j) {
+    // exact by construction: every eligible row is rescored canonically and the k best are selected
+    auto list_query = [&](int j) {
         if (m)
             orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)j * ORX_DIM, ix->prep.p + j,
                                      ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, st);
         orx::launch_select_list(ix->row_ids, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, k, out.ids + (size_t)j * k,
                                 out.dist + (size_t)j * k, out.counts + j, st);
         ix->stats.kernel_launches += m ? 2 : 1;
+    };
+    const int slots = orx::slots_for_k(k);
+    if (m >= FILTER_SCAN_MIN_ROWS && m > 32u * (uint32_t)slots) {
+        // many eligible rows: the predicate becomes a row bitmap and the sequential scan skips the rows
+        // whose bit is clear (HBM traffic = eligible rows only); same candidate proof as orx_search,
+        // the rare unproven query is re-answered by the exact list path.
+        const uint32_t n_rows = (uint32_t)ix->n_live;
+        const size_t n_words = ((size_t)n_rows + 31) / 32;
+        CK(ix->h_allow_bits.ensure(n_words));
+        CK(ix->allow_bits.ensure(n_words));
+        memset(ix->h_allow_bits.p, 0, n_words * sizeof(uint32_t));
+        for (uint32_t r : rows) ix->h_allow_bits.p[r >> 5] |= 1u << (r & 31);
+        CK(cudaMemcpyAsync(ix->allow_bits.p, ix->h_allow_bits.p, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(ix->h_flags.ensure(nq));
+        const int grid = orx::scan_gemv_grid(ix->device, n_rows);
+        const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
+        ix->scan_ev_used = 0;
+        for (int s0 = 0; s0 < nq; s0 += GEMV_QCHUNK) {
+            const int mq = std::min(GEMV_QCHUNK, nq - s0);
+            CK(ix->partial.ensure((size_t)mq * grid * 32 * slots));
+            cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
+            if (e0 && e1) CK(cudaEventRecord(e0, st));
+            orx::launch_scan_gemv_filtered(ix->dtype, ix->table, ix->scale, n_rows, ix->allow_bits.p,
+                                           ix->qhat.p + (size_t)s0 * ORX_DIM, mq, slots, ix->partial.p, grid, st);
+            if (e0 && e1) CK(cudaEventRecord(e1, st));
+            // n_rows argument = the eligible count: "every eligible row is a candidate" when it fits the list
+            orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)s0 * ORX_DIM, ix->prep.p + s0,
+                                 ix->partial.p, grid, slots, mq, k, m, eps, out.ids + (size_t)s0 * k,
+                                 out.dist + (size_t)s0 * k, out.counts + s0, ix->h_flags.p + s0, st);
+            ix->stats.kernel_launches += 2;
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        harvest_scan_events(ix);
+        ix->stats.last_path = 1;
+        for (int j = 0; j < nq; ++j) {
+            if (!(ix->h_flags.p[j] & 1) || (ix->h_flags.p[j] & 2)) continue;
+            ix->stats.fallback_exhaustive += 1;
+            list_query(j);
+        }
+    } else {
+        // few rows: no scan at all
+        for (int j = 0; j < nq; ++j) list_query(j);
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());

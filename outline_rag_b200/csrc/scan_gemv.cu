@@ -90,6 +90,98 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
     if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
 }
 
+// ------------------------------------------------------------------ filtered scan
+// The same scan restricted to the rows whose bit is set in `allow_bits` (bit r%32 of word r/32; bits at
+// or beyond n_rows are 0): the SQL with a WHERE clause once the predicate is resolved to rows
+// (orx_search_filtered, SURVEY.md 8f-4 "bitmap AND pushed into the scan").  Work unit = one bitmap word
+// = 32 consecutive rows per warp; rows whose bit is clear are never loaded, so HBM traffic is
+// eligible_rows * row_bytes.  Scores come from the same instruction sequence as the unfiltered scan
+// (scan_common.cuh), so the same error bound and the same completeness proof apply.
+// (The per-CTA merge below restates the one inside scan_gemv_kernel, which is left textually as it was
+// measured: folding both into one helper changes that kernel's register allocation.)
+template <int S>
+__device__ __forceinline__ void cta_merge_store(const WarpTopK<S> &top, uint64_t (&s_keys)[SCAN_WARPS][32 * S],
+                                                uint64_t *__restrict__ partial, int lane, int warp) {
+    constexpr int K = 32 * S;
+    top.store(s_keys[warp], lane);
+    __syncthreads();
+    const uint64_t *all = &s_keys[0][0];
+    constexpr int TOTAL = SCAN_WARPS * K;
+    int nonzero = 0;
+#pragma unroll
+    for (int h = 0; h < TOTAL / SCAN_THREADS; ++h) {
+        const uint64_t mine = all[threadIdx.x + h * SCAN_THREADS];
+        nonzero += (mine != 0ull);
+        if (mine == 0ull) continue;
+        int rank = 0;
+#pragma unroll 8
+        for (int i = 0; i < TOTAL; ++i) rank += (all[i] > mine);
+        if (rank < K) partial[rank] = mine;
+    }
+    int nnz = 0;
+#pragma unroll
+    for (int j = 1; j <= TOTAL / SCAN_THREADS; ++j) nnz += __syncthreads_count(nonzero >= j);
+    if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
+}
+
+template <typename T, int S>
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
+scan_gemv_filtered_kernel(const T *__restrict__ table, const float *__restrict__ scale, uint32_t n_rows,
+                          const uint32_t *__restrict__ allow_bits, const float *__restrict__ qhat_all,
+                          uint64_t *__restrict__ partial_all) {
+    constexpr int NV = RowVec<T>::NV;
+    constexpr int ROWS_PER_ITER = RowsPerIter<T>::value;
+    constexpr int K = 32 * S;
+    __shared__ uint64_t s_keys[SCAN_WARPS][K];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int query = blockIdx.y;
+    const float *qhat = qhat_all + (size_t)query * ORX_DIM;
+    uint64_t *partial = partial_all + ((size_t)query * gridDim.x + blockIdx.x) * K;
+
+    float4 qv[8];
+    load_q_slice<T>(qhat, lane, qv);
+
+    WarpTopK<S> top;
+    top.init();
+
+    const uint4 *tab = reinterpret_cast<const uint4 *>(table);
+    const uint32_t gw = blockIdx.x * SCAN_WARPS + warp;
+    const uint32_t n_gw = gridDim.x * SCAN_WARPS;
+    const uint32_t n_groups = (n_rows + 31) / 32;
+
+    uint32_t w_next = gw < n_groups ? __ldg(allow_bits + gw) : 0u;
+    for (uint32_t g = gw; g < n_groups; g += n_gw) {
+        uint32_t w = w_next;                                        // warp-uniform
+        w_next = g + n_gw < n_groups ? __ldg(allow_bits + g + n_gw) : 0u;   // in flight while this group streams
+        while (w) {
+            uint4 v[ROWS_PER_ITER][NV];
+            float sc[ROWS_PER_ITER];
+            uint32_t row[ROWS_PER_ITER];
+            bool ok[ROWS_PER_ITER];
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_ITER; ++r) {
+                ok[r] = w != 0u;
+                row[r] = g * 32u + (ok[r] ? (uint32_t)(__ffs(w) - 1) : 0u);
+                w &= w - 1u;                                        // 0 stays 0
+                if (ok[r]) {
+                    load_row_vecs<T>(tab, row[r], lane, v[r]);
+                    sc[r] = __ldg(scale + row[r]);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS_PER_ITER; ++r) {
+                if (ok[r] && row[r] < n_rows) {
+                    const float acc = warp_row_dot<T>(v[r], qv);
+                    top.offer(make_key(score_ord(acc, sc[r]), row[r]), lane);
+                }
+            }
+        }
+    }
+    cta_merge_store<S>(top, s_keys, partial, lane, warp);
+}
+
 int scan_gemv_grid(int device, uint32_t n_rows) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -121,6 +213,29 @@ void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t
         launch_scan_gemv_t<float>(table, scale, n_rows, qhat, nq, slots, partial, grid, st);
     else
         launch_scan_gemv_t<__nv_bfloat16>(table, scale, n_rows, qhat, nq, slots, partial, grid, st);
+}
+
+template <typename T>
+static void launch_scan_gemv_filtered_t(const void *table, const float *scale, uint32_t n_rows,
+                                        const uint32_t *allow_bits, const float *qhat, int nq, int slots,
+                                        uint64_t *partial, int grid, cudaStream_t st) {
+    dim3 g(grid, nq);
+    const T *tab = static_cast<const T *>(table);
+    switch (slots) {
+        case 1: scan_gemv_filtered_kernel<T, 1><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, allow_bits, qhat, partial); break;
+        case 2: scan_gemv_filtered_kernel<T, 2><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, allow_bits, qhat, partial); break;
+        case 4: scan_gemv_filtered_kernel<T, 4><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, allow_bits, qhat, partial); break;
+        default: scan_gemv_filtered_kernel<T, 5><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, allow_bits, qhat, partial); break;
+    }
+}
+
+void launch_scan_gemv_filtered(int dtype, const void *table, const float *scale, uint32_t n_rows,
+                               const uint32_t *allow_bits, const float *qhat, int nq, int slots,
+                               uint64_t *partial, int grid, cudaStream_t st) {
+    if (dtype == ORX_DTYPE_F32)
+        launch_scan_gemv_filtered_t<float>(table, scale, n_rows, allow_bits, qhat, nq, slots, partial, grid, st);
+    else
+        launch_scan_gemv_filtered_t<__nv_bfloat16>(table, scale, n_rows, allow_bits, qhat, nq, slots, partial, grid, st);
 }
 
 }  // namespace orx

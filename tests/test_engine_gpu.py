@@ -600,6 +600,52 @@ def test_filtered_search_is_the_sql_with_a_where_clause(Index, small_table):
             ix.search_filtered(bad, K, ids[:5])
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_filtered_search_with_many_eligible_rows_scans_through_a_row_bitmap(Index, small_table, dtype):
+    """>= 4096 eligible rows: the predicate becomes a bitmap and the sequential scan skips the other rows
+    (csrc/scan_gemv.cu scan_gemv_filtered_kernel).  Same answers as the oracle on the eligible subset."""
+    X, Q, _ = small_table                                      # 8192 rows
+    n = X.shape[0]
+    X = X.copy()
+    X[4000] = 0.0                                              # eligible zero-norm row
+    X[100:140] = X[99]                                         # 41 identical eligible rows: a tie wider than the list
+    ids = _ids(n, 1000)
+    rows = X if dtype == "fp32" else stored_bf16_rows(X)
+    rng = np.random.default_rng(21)
+    with Index(dtype) as ix:
+        ix.upsert(ids, X)
+        for m in (4096, 5000, n):
+            sel = np.sort(rng.choice(n, size=m, replace=False))
+            if m < n:
+                sel = np.unique(np.concatenate([sel, np.arange(99, 140), [4000]]))
+            queries = np.concatenate([Q[:4], X[99:100], np.zeros((1, DIM), np.float32)])   # a tie query, a zero query
+            for k in (K, 40):
+                launches0 = ix.stats()["scan_launches"]
+                g_ids, g_d, g_c = ix.search_filtered(queries, k, ids[rng.permutation(sel)])
+                assert ix.stats()["scan_launches"] > launches0                              # the scan ran
+                for i in range(queries.shape[0]):
+                    w_ids, w_d = O.topk_exact(rows[sel], ids[sel], queries[i], k, exhaustive=True)
+                    assert g_c[i] == k
+                    assert np.array_equal(g_ids[i], w_ids), (m, k, i)
+                    nan = np.isnan(w_d)
+                    assert np.array_equal(np.isnan(g_d[i]), nan), (m, k, i)
+                    assert np.array_equal(g_d[i][~nan].view(np.uint64), w_d[~nan].view(np.uint64)), (m, k, i)
+        # every row eligible == the unfiltered search
+        a = ix.search(Q[:8], K)
+        b = ix.search_filtered(Q[:8], K, ids)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
+        # the bitmap follows deletes (rows move) because it is rebuilt from the ids on every call
+        gone = ids[sel[:50]]
+        ix.delete(gone)
+        keep = np.ones(n, bool)
+        keep[sel[:50]] = False
+        sel2 = np.array([r for r in sel if keep[r]])
+        g_ids, g_d, _ = ix.search_filtered(Q[:2], K, ids[sel])                              # deleted ids are unknown now
+        for i in range(2):
+            w_ids, w_d = O.topk_exact(rows[sel2], ids[sel2], Q[i], K, exhaustive=True)
+            assert np.array_equal(g_ids[i], w_ids) and np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64))
+
+
 def test_large_k_for_a_wider_reranker_feed(Index, small_table):
     """k up to 128 (SURVEY.md 8f-4): batches stay exact (fp32 scan per query), ties and short tables too;
     the sharded exchange chunks the batch so that a slot still fits."""
