@@ -115,6 +115,18 @@ int orx_search_filtered(orx_index *idx, const float *queries, int nq, int dim, i
                         const orx_id *allow_ids, uint64_t n_allow,
                         orx_id *out_ids, double *out_dist, int *out_counts);
 
+/* A reusable predicate: resolving every allowed id to its row costs one hash look-up per id, which for
+ * large allow-lists is far more than the scan itself (measured: 115 ms vs 1.2 ms for 2M ids).  A filter
+ * keeps the resolved rows (list + bitmap) on the device between searches; it is re-resolved
+ * automatically when the id -> row map has changed (upsert of new ids, delete, import), so it always
+ * denotes "the live rows whose id is in the set".  orx_search_with_filter == orx_search_filtered with the
+ * ids the filter was created from.  Destroy filters before their index. */
+typedef struct orx_filter orx_filter;
+int orx_filter_create(orx_index *idx, const orx_id *allow_ids, uint64_t n_allow, orx_filter **out);
+void orx_filter_destroy(orx_filter *flt);
+int orx_search_with_filter(orx_index *idx, orx_filter *flt, const float *queries, int nq, int dim, int k,
+                           orx_id *out_ids, double *out_dist, int *out_counts);
+
 /* Merge `n_lists` per-shard results (each [nq, k] as written by orx_search, all on
  * this index's device or all on the host) into the global top-k with the same
  * ordering.  The on-device step after the NCCL allgather of the row-sharded path. */

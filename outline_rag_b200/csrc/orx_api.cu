@@ -146,6 +146,7 @@ struct orx_index {
     cudaStream_t stream = nullptr;
     uint64_t capacity = 0;
     uint64_t n_live = 0;
+    uint64_t generation = 0;            // bumped whenever the id -> row map changes (orx_filter re-resolves then)
     int scan_grid_sms = 148;
 
     // the table (device)
@@ -188,6 +189,16 @@ struct orx_index {
     orx::UmmaPlan *umma = nullptr;
     mutable std::mutex mu;
     orx_stats stats{};
+};
+
+struct orx_filter {     // a reusable resolved predicate (orx_filter_create / orx_search_with_filter)
+    orx_index *ix = nullptr;
+    int device = 0;
+    std::vector<orx_id> ids;              // the id set as given
+    DevBuf<uint32_t> d_list, d_count, d_bits;
+    uint32_t m = 0;                       // eligible live rows at `generation`
+    uint64_t generation = 0;
+    bool resolved = false;
 };
 
 namespace {
@@ -507,6 +518,143 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
     return ORX_OK;
 }
 
+
+// =========================================================================== filtered search
+struct FilterOnDevice {          // a resolved predicate: the eligible rows, as a sorted list and (when large) a bitmap
+    uint32_t m;
+    const uint32_t *list;        // [m] device
+    const uint32_t *count;       // device word holding m
+    const uint32_t *bits;        // [(n_live+31)/32] device, or null: rescore the list, no scan
+};
+
+int check_filtered_args(orx_index *ix, const float *queries, int nq, int dim, int k, orx_id *out_ids, double *out_dist,
+                        int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "different vector dimensions %d and %d", ORX_DIM, dim);
+    if (k < 1 || k > ORX_MAX_K) return fail(ORX_ERR_INVALID, "k must be in [1, %d], got %d", ORX_MAX_K, k);
+    if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
+    if (nq == 0) return ORX_OK;
+    if (!queries || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    return ORX_OK;
+}
+
+// the eligible rows: ids that are live, each row once (the WHERE clause of the SQL), ascending
+void resolve_allow_ids(const orx_index *ix, const orx_id *ids, uint64_t n, std::vector<uint32_t> &rows) {
+    rows.clear();
+    rows.reserve(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        auto it = ix->map.find(ids[i]);
+        if (it != ix->map.end()) rows.push_back(it->second);
+    }
+    std::sort(rows.begin(), rows.end());
+    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
+}
+
+int upload_filter(orx_index *ix, const std::vector<uint32_t> &rows, DevBuf<uint32_t> &list, DevBuf<uint32_t> &count,
+                  DevBuf<uint32_t> &bits) {
+    cudaStream_t st = ix->stream;
+    const uint32_t m = (uint32_t)rows.size();
+    CK(list.ensure(std::max<size_t>(m, 1)));
+    CK(count.ensure(1));
+    CK(ix->h_u32a.ensure(1));
+    *ix->h_u32a.p = m;
+    if (m) CK(cudaMemcpyAsync(list.p, rows.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(count.p, ix->h_u32a.p, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (m >= FILTER_SCAN_MIN_ROWS) {
+        const size_t n_words = ((size_t)ix->n_live + 31) / 32;
+        CK(ix->h_allow_bits.ensure(n_words));
+        CK(bits.ensure(n_words));
+        memset(ix->h_allow_bits.p, 0, n_words * sizeof(uint32_t));
+        for (uint32_t r : rows) ix->h_allow_bits.p[r >> 5] |= 1u << (r & 31);
+        CK(cudaMemcpyAsync(bits.p, ix->h_allow_bits.p, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));          // `rows` and the pinned scratch may be reused by the caller
+    return ORX_OK;
+}
+
+int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *queries, int nq, int k, orx_id *out_ids,
+                           double *out_dist, int *out_counts) {
+    cudaStream_t st = ix->stream;
+    const bool out_on_dev = is_device_ptr(out_ids);
+    if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
+        return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
+    const size_t nk = (size_t)nq * k;
+    const uint32_t m = f.m;
+
+    const float *q_src = nullptr;
+    int rc = stage_queries(ix, queries, nq, &q_src);
+    if (rc != ORX_OK) return rc;
+    CK(ix->h_prep.ensure(nq));
+    CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
+    if (!out_on_dev) {
+        CK(ix->h_ids.ensure(nk));
+        CK(ix->h_dist.ensure(nk));
+        CK(ix->h_counts.ensure(nq));
+    }
+    SearchOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                  out_on_dev ? out_counts : ix->h_counts.p};
+    CK(ix->fb_dist.ensure(std::max<size_t>(m, 1)));
+    // exact by construction: every eligible row is rescored canonically and the k best are selected
+    auto list_query = [&](int j) {
+        if (m)
+            orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)j * ORX_DIM, ix->prep.p + j,
+                                     f.list, f.count, ix->fb_dist.p, st);
+        orx::launch_select_list(ix->row_ids, f.list, f.count, ix->fb_dist.p, k, out.ids + (size_t)j * k,
+                                out.dist + (size_t)j * k, out.counts + j, st);
+        ix->stats.kernel_launches += m ? 2 : 1;
+    };
+    const int slots = orx::slots_for_k(k);
+    if (f.bits != nullptr && m > 32u * (uint32_t)slots) {
+        // many eligible rows: the predicate is a row bitmap and the sequential scan skips the rows whose
+        // bit is clear (HBM traffic = eligible rows only); same candidate proof as orx_search, the rare
+        // unproven query is re-answered by the exact list path.
+        const uint32_t n_rows = (uint32_t)ix->n_live;
+        CK(ix->h_flags.ensure(nq));
+        const int grid = orx::scan_gemv_grid(ix->device, n_rows);
+        const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
+        ix->scan_ev_used = 0;
+        for (int s0 = 0; s0 < nq; s0 += GEMV_QCHUNK) {
+            const int mq = std::min(GEMV_QCHUNK, nq - s0);
+            CK(ix->partial.ensure((size_t)mq * grid * 32 * slots));
+            cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
+            if (e0 && e1) CK(cudaEventRecord(e0, st));
+            orx::launch_scan_gemv_filtered(ix->dtype, ix->table, ix->scale, n_rows, f.bits,
+                                           ix->qhat.p + (size_t)s0 * ORX_DIM, mq, slots, ix->partial.p, grid, st);
+            if (e0 && e1) CK(cudaEventRecord(e1, st));
+            // n_rows argument = the eligible count: "every eligible row is a candidate" when it fits the list
+            orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)s0 * ORX_DIM, ix->prep.p + s0,
+                                 ix->partial.p, grid, slots, mq, k, m, eps, out.ids + (size_t)s0 * k,
+                                 out.dist + (size_t)s0 * k, out.counts + s0, ix->h_flags.p + s0, st);
+            ix->stats.kernel_launches += 2;
+        }
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        harvest_scan_events(ix);
+        ix->stats.last_path = 1;
+        for (int j = 0; j < nq; ++j) {
+            if (!(ix->h_flags.p[j] & 1) || (ix->h_flags.p[j] & 2)) continue;
+            ix->stats.fallback_exhaustive += 1;
+            list_query(j);
+        }
+    } else {
+        // few rows: no scan at all
+        for (int j = 0; j < nq; ++j) list_query(j);
+    }
+    CK(cudaStreamSynchronize(st));
+    CK(cudaGetLastError());
+    for (int j = 0; j < nq; ++j)
+        if (ix->h_prep.p[j].nonfinite)
+            return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+    if (!out_on_dev) {
+        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
+        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
+        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
+    }
+    ix->stats.searches += 1;
+    ix->stats.queries += nq;
+    return ORX_OK;
+}
+
 // =========================================================================== sharded search
 // Layout of one rank's result block for (nq, k): ids | dist | counts | flags (16-byte padded).
 struct SlotLayout {
@@ -799,6 +947,7 @@ int orx_upsert(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t n, 
     }
     int rc = grow_table(ix, ix->n_live + n_new);
     if (rc != ORX_OK) return rc;
+    if (n_new) ix->generation += 1;
 
     CK(ix->d_src_idx.ensure(chunk));
     CK(ix->d_dst_row.ensure(chunk));
@@ -891,6 +1040,7 @@ int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed
     }
     ix->host_row_ids.resize(new_live);
     ix->n_live = new_live;
+    ix->generation += 1;
     if (hmv > 0) {
         CK(ix->d_src_idx.ensure(hmv));
         CK(ix->d_dst_row.ensure(hmv));
@@ -922,113 +1072,64 @@ int orx_search(orx_index *ix, const float *queries, int nq, int dim, int k, orx_
 
 int orx_search_filtered(orx_index *ix, const float *queries, int nq, int dim, int k, const orx_id *allow_ids,
                         uint64_t n_allow, orx_id *out_ids, double *out_dist, int *out_counts) {
-    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
-    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "different vector dimensions %d and %d", ORX_DIM, dim);
-    if (k < 1 || k > ORX_MAX_K) return fail(ORX_ERR_INVALID, "k must be in [1, %d], got %d", ORX_MAX_K, k);
-    if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
-    if (nq == 0) return ORX_OK;
-    if (!queries || !out_ids || !out_dist || !out_counts || (n_allow && !allow_ids)) return fail(ORX_ERR_INVALID, "null argument");
+    int rc = check_filtered_args(ix, queries, nq, dim, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK || nq == 0) return rc;
+    if (n_allow && !allow_ids) return fail(ORX_ERR_INVALID, "null argument");
     if (is_device_ptr(allow_ids)) return fail(ORX_ERR_INVALID, "allow_ids must be a host pointer");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
-    const bool out_on_dev = is_device_ptr(out_ids);
-    if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
-        return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
-    const size_t nk = (size_t)nq * k;
-    // the eligible rows: ids that are live, each row once (the WHERE clause of the SQL)
     std::vector<uint32_t> rows;
-    rows.reserve(n_allow);
-    for (uint64_t i = 0; i < n_allow; ++i) {
-        auto it = ix->map.find(allow_ids[i]);
-        if (it != ix->map.end()) rows.push_back(it->second);
-    }
-    std::sort(rows.begin(), rows.end());
-    rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
-    const uint32_t m = (uint32_t)rows.size();
-
-    const float *q_src = nullptr;
-    int rc = stage_queries(ix, queries, nq, &q_src);
+    resolve_allow_ids(ix, allow_ids, n_allow, rows);
+    rc = upload_filter(ix, rows, ix->fb_list, ix->fb_count, ix->allow_bits);
     if (rc != ORX_OK) return rc;
-    CK(ix->h_prep.ensure(nq));
-    CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
-    if (!out_on_dev) {
-        CK(ix->h_ids.ensure(nk));
-        CK(ix->h_dist.ensure(nk));
-        CK(ix->h_counts.ensure(nq));
-    }
-    SearchOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                  out_on_dev ? out_counts : ix->h_counts.p};
-    CK(ix->fb_list.ensure(std::max<size_t>(m, 1)));
-    CK(ix->fb_dist.ensure(std::max<size_t>(m, 1)));
-    CK(ix->fb_count.ensure(1));
-    if (m) CK(cudaMemcpyAsync(ix->fb_list.p, rows.data(), m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ix->fb_count.p, &m, sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    // exact by construction: every eligible row is rescored canonically and the k best are selected
-    auto list_query = [&](int j) {
-        if (m)
-            orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)j * ORX_DIM, ix->prep.p + j,
-                                     ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, st);
-        orx::launch_select_list(ix->row_ids, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, k, out.ids + (size_t)j * k,
-                                out.dist + (size_t)j * k, out.counts + j, st);
-        ix->stats.kernel_launches += m ? 2 : 1;
-    };
-    const int slots = orx::slots_for_k(k);
-    if (m >= FILTER_SCAN_MIN_ROWS && m > 32u * (uint32_t)slots) {
-        // many eligible rows: the predicate becomes a row bitmap and the sequential scan skips the rows
-        // whose bit is clear (HBM traffic = eligible rows only); same candidate proof as orx_search,
-        // the rare unproven query is re-answered by the exact list path.
-        const uint32_t n_rows = (uint32_t)ix->n_live;
-        const size_t n_words = ((size_t)n_rows + 31) / 32;
-        CK(ix->h_allow_bits.ensure(n_words));
-        CK(ix->allow_bits.ensure(n_words));
-        memset(ix->h_allow_bits.p, 0, n_words * sizeof(uint32_t));
-        for (uint32_t r : rows) ix->h_allow_bits.p[r >> 5] |= 1u << (r & 31);
-        CK(cudaMemcpyAsync(ix->allow_bits.p, ix->h_allow_bits.p, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CK(ix->h_flags.ensure(nq));
-        const int grid = orx::scan_gemv_grid(ix->device, n_rows);
-        const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
-        ix->scan_ev_used = 0;
-        for (int s0 = 0; s0 < nq; s0 += GEMV_QCHUNK) {
-            const int mq = std::min(GEMV_QCHUNK, nq - s0);
-            CK(ix->partial.ensure((size_t)mq * grid * 32 * slots));
-            cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
-            if (e0 && e1) CK(cudaEventRecord(e0, st));
-            orx::launch_scan_gemv_filtered(ix->dtype, ix->table, ix->scale, n_rows, ix->allow_bits.p,
-                                           ix->qhat.p + (size_t)s0 * ORX_DIM, mq, slots, ix->partial.p, grid, st);
-            if (e0 && e1) CK(cudaEventRecord(e1, st));
-            // n_rows argument = the eligible count: "every eligible row is a candidate" when it fits the list
-            orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)s0 * ORX_DIM, ix->prep.p + s0,
-                                 ix->partial.p, grid, slots, mq, k, m, eps, out.ids + (size_t)s0 * k,
-                                 out.dist + (size_t)s0 * k, out.counts + s0, ix->h_flags.p + s0, st);
-            ix->stats.kernel_launches += 2;
-        }
-        CK(cudaStreamSynchronize(st));
-        CK(cudaGetLastError());
-        harvest_scan_events(ix);
-        ix->stats.last_path = 1;
-        for (int j = 0; j < nq; ++j) {
-            if (!(ix->h_flags.p[j] & 1) || (ix->h_flags.p[j] & 2)) continue;
-            ix->stats.fallback_exhaustive += 1;
-            list_query(j);
-        }
-    } else {
-        // few rows: no scan at all
-        for (int j = 0; j < nq; ++j) list_query(j);
-    }
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    for (int j = 0; j < nq; ++j)
-        if (ix->h_prep.p[j].nonfinite)
-            return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
-    if (!out_on_dev) {
-        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
-        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
-        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
-    }
-    ix->stats.searches += 1;
-    ix->stats.queries += nq;
+    const uint32_t m = (uint32_t)rows.size();
+    const FilterOnDevice f{m, ix->fb_list.p, ix->fb_count.p, m >= FILTER_SCAN_MIN_ROWS ? ix->allow_bits.p : nullptr};
+    return filtered_search_locked(ix, f, queries, nq, k, out_ids, out_dist, out_counts);
+}
+
+int orx_filter_create(orx_index *ix, const orx_id *allow_ids, uint64_t n_allow, orx_filter **out) {
+    if (!out) return fail(ORX_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (n_allow && !allow_ids) return fail(ORX_ERR_INVALID, "null argument");
+    if (is_device_ptr(allow_ids)) return fail(ORX_ERR_INVALID, "allow_ids must be a host pointer");
+    orx_filter *f = new orx_filter();
+    f->ix = ix;
+    f->device = ix->device;
+    f->ids.assign(allow_ids, allow_ids + n_allow);
+    *out = f;
     return ORX_OK;
+}
+
+void orx_filter_destroy(orx_filter *f) {
+    if (!f) return;
+    DeviceGuard g(f->device);
+    f->d_list.release();
+    f->d_count.release();
+    f->d_bits.release();
+    cudaGetLastError();
+    delete f;
+}
+
+int orx_search_with_filter(orx_index *ix, orx_filter *f, const float *queries, int nq, int dim, int k,
+                           orx_id *out_ids, double *out_dist, int *out_counts) {
+    int rc = check_filtered_args(ix, queries, nq, dim, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK || nq == 0) return rc;
+    if (!f || f->ix != ix) return fail(ORX_ERR_INVALID, "filter does not belong to this index");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!f->resolved || f->generation != ix->generation) {
+        // the id -> row map changed since the bitmap was built (upsert of new ids, delete, import)
+        std::vector<uint32_t> rows;
+        resolve_allow_ids(ix, f->ids.data(), f->ids.size(), rows);
+        rc = upload_filter(ix, rows, f->d_list, f->d_count, f->d_bits);
+        if (rc != ORX_OK) return rc;
+        f->m = (uint32_t)rows.size();
+        f->generation = ix->generation;
+        f->resolved = true;
+    }
+    const FilterOnDevice fd{f->m, f->d_list.p, f->d_count.p, f->m >= FILTER_SCAN_MIN_ROWS ? f->d_bits.p : nullptr};
+    return filtered_search_locked(ix, fd, queries, nq, k, out_ids, out_dist, out_counts);
 }
 
 int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids, const double *dist,
@@ -1147,6 +1248,7 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
         ix->map.emplace(ids[i], (uint32_t)(row0 + i));
     }
     ix->n_live = row0 + n;
+    ix->generation += 1;
     return ORX_OK;
 }
 

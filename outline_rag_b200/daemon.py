@@ -116,6 +116,10 @@ class IndexServer:
                 else:
                     ids, dist, cnt = await asyncio.to_thread(self.index.search, Q, k)
                 return {"ids": _pack_arr(ids), "dist": _pack_arr(dist), "cnt": _pack_arr(cnt)}
+            if op == "search_filtered":
+                ids, dist, cnt = await asyncio.to_thread(self.index.search_filtered, _unpack_arr(req["q"]), int(req["k"]),
+                                                         _unpack_arr(req["allow"]))
+                return {"ids": _pack_arr(ids), "dist": _pack_arr(dist), "cnt": _pack_arr(cnt)}
             if op == "upsert":
                 async with self._write_lock:
                     await asyncio.to_thread(self.index.upsert, _unpack_arr(req["ids"]), _unpack_arr(req["vecs"]))
@@ -210,6 +214,16 @@ class RemoteIndex:
         if q.ndim == 1:
             q = q.reshape(1, -1)
         r = self._call({"op": "search", "q": _pack_arr(q), "k": int(k)})
+        return _unpack_arr(r["ids"]), _unpack_arr(r["dist"]), _unpack_arr(r["cnt"])
+
+    def search_filtered(self, queries, k: int, allow_ids):
+        """`Index.search_filtered` on the owner (ids are resolved there on every call; device-resident
+        `Filter` handles live in the owner process and do not cross the socket)."""
+        from .engine import ids_to_array
+        q = np.asarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q.reshape(1, -1)
+        r = self._call({"op": "search_filtered", "q": _pack_arr(q), "k": int(k), "allow": _pack_arr(ids_to_array(allow_ids))})
         return _unpack_arr(r["ids"]), _unpack_arr(r["dist"]), _unpack_arr(r["cnt"])
 
     def upsert(self, ids, vecs) -> None:

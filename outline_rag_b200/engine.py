@@ -90,6 +90,34 @@ def parse_vector_text(text, dim: int = ORX_DIM) -> np.ndarray:
     return out
 
 
+class Filter:
+    """A reusable predicate on chunk ids (`orx_filter_*`): the id -> row resolution and the row bitmap stay
+    on the device between searches and follow upserts / deletes.  Pass it to `Index.search_filtered`."""
+
+    def __init__(self, index: "Index", allow_ids):
+        self._f = C.c_void_p()
+        self._index = index
+        ida = ids_to_array(allow_ids)
+        check(lib.orx_filter_create(index._h, C.c_void_p(ida.ctypes.data), ida.shape[0], C.byref(self._f)))
+
+    def close(self) -> None:
+        if getattr(self, "_f", None) is not None and self._f:
+            lib.orx_filter_destroy(self._f)
+            self._f = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 class PgCopyLoader:
     """Streaming cold-start load from ``COPY (SELECT langchain_id, embedding FROM langchain_pg_embedding)
     TO STDOUT (FORMAT binary)`` (`orx_pgcopy_*`; table: reference app/database.py:118-131).
@@ -259,14 +287,25 @@ class Index:
                              C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
         return ids, dist, cnt
 
+    def make_filter(self, allow_ids) -> Filter:
+        return Filter(self, allow_ids)
+
     def search_filtered(self, queries, k: int, allow_ids):
-        """Exact top-k among the given chunk ids only (`WHERE langchain_id IN (...)`); NumPy in/out."""
+        """Exact top-k among the given chunk ids only (`WHERE langchain_id IN (...)`); NumPy in/out.
+        `allow_ids`: ids (resolved on every call) or a `Filter` (resolved once, kept on the device)."""
         q = _host_f32(queries, "queries")
         nq, dim = q.shape
-        allow = ids_to_array(allow_ids)
         ids = np.zeros((nq, max(k, 0), 2), np.uint64)
         dist = np.full((nq, max(k, 0)), np.nan, np.float64)
         cnt = np.zeros(nq, np.int32)
+        if isinstance(allow_ids, Filter):
+            if allow_ids._index is not self or not allow_ids._f:
+                raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "filter is closed or belongs to another index")
+            check(lib.orx_search_with_filter(self._h, allow_ids._f, C.c_void_p(q.ctypes.data), nq, dim, int(k),
+                                             C.c_void_p(ids.ctypes.data), C.c_void_p(dist.ctypes.data),
+                                             C.c_void_p(cnt.ctypes.data)))
+            return ids, dist, cnt
+        allow = ids_to_array(allow_ids)
         check(lib.orx_search_filtered(self._h, C.c_void_p(q.ctypes.data), nq, dim, int(k),
                                       C.c_void_p(allow.ctypes.data), allow.shape[0], C.c_void_p(ids.ctypes.data),
                                       C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
@@ -424,4 +463,4 @@ def synth_rows_device(device: int, seed: int, n_centres: int, row_start: int, n_
     return out
 
 
-__all__ = ["Index", "PgCopyLoader", "parse_vector_text", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device"]
+__all__ = ["Index", "Filter", "PgCopyLoader", "parse_vector_text", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device"]

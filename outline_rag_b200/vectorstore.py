@@ -27,7 +27,7 @@ from typing import Any, Iterable, Optional, Sequence
 import numpy as np
 
 from .batcher import QueryBatcher
-from .engine import Index, ids_to_array, ids_to_uuid_strs
+from .engine import Filter, Index, ids_to_array, ids_to_uuid_strs
 
 try:  # use the real class when the host application has langchain installed
     from langchain_core.documents import Document  # type: ignore
@@ -254,11 +254,19 @@ class GpuVectorStore:
         q = np.asarray(embedding, dtype=np.float32).reshape(1, -1)
         if filter is not None:
             # the metadata predicate is resolved where the metadata lives (doc store / Postgres), the
-            # similarity ordering of the eligible chunks runs on the GPU (orx_search_filtered)
-            ids, dist, cnt = self.index.search_filtered(q, k, self.doc_store.ids_for_filter(filter))
+            # similarity ordering of the eligible chunks runs on the GPU (orx_search_filtered); a prepared
+            # filter (`prepare_filter`) skips both the look-up and the id -> row resolution
+            allow = filter if isinstance(filter, Filter) else self.doc_store.ids_for_filter(filter)
+            ids, dist, cnt = self.index.search_filtered(q, k, allow)
         else:
             ids, dist, cnt = self.index.search(q, k)
         return self._hydrate(ids[0], dist[0], int(cnt[0]))
+
+    def prepare_filter(self, filter: dict) -> Filter:
+        """Resolve a metadata predicate ONCE into a device-resident `Filter` that can be passed as `filter=`
+        to every later search (a collection- or source-scoped assistant asks the same predicate each time).
+        It denotes the chunk ids matching NOW; chunks added later need a new `prepare_filter`."""
+        return self.index.make_filter(self.doc_store.ids_for_filter(filter))
 
     def batch_search_by_vector(self, embeddings, k: int = 4):
         """Many queries in one scan (the micro-batching front end of SURVEY.md 8f-3 calls this)."""

@@ -29,6 +29,12 @@ class FakeOwner(FakeIndex):
         self.ids = np.concatenate([self.ids, np.asarray(ids, np.uint64).reshape(-1, 2)])
         self.X = np.concatenate([self.X, np.asarray(vecs, np.float32)])
 
+    def search_filtered(self, Q, k, allow):
+        self.log.append(("search_filtered", len(allow)))
+        ok = {tuple(map(int, r)) for r in np.asarray(allow, np.uint64).reshape(-1, 2)}
+        keep = np.array([tuple(map(int, r)) in ok for r in self.ids], bool)
+        return FakeIndex(self.X[keep], self.ids[keep]).search(np.asarray(Q, np.float32), k)
+
     def delete(self, ids):
         kill = {tuple(map(int, r)) for r in np.asarray(ids, np.uint64).reshape(-1, 2)}
         keep = np.array([tuple(map(int, r)) not in kill for r in self.ids], bool)
@@ -66,6 +72,11 @@ def test_two_workers_share_one_owner(small_table, tmp_path):
         got = b.search(X[601], 1)
         assert O.ids_to_ints(got[0][0]) == [901]
         assert owner.log == [("upsert", 3), ("delete", 2)]
+        # the WHERE-clause search crosses the socket too
+        f_ids, f_d, f_c = a.search_filtered(Q[0], 5, O.ids_arange(100, 140))
+        w_ids, w_d = O.topk_exact(X[100:140], O.ids_arange(100, 140), Q[0], 5)
+        assert f_c[0] == 5 and np.array_equal(f_ids[0], w_ids) and np.array_equal(f_d[0], w_d)
+        assert owner.log[-1] == ("search_filtered", 40)
         with pytest.raises(orx.OrxValueError, match="dimensions"):
             a.search(np.zeros((1, 100), np.float32), 12)
         with pytest.raises(orx.OrxValueError):

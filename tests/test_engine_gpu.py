@@ -646,6 +646,51 @@ def test_filtered_search_with_many_eligible_rows_scans_through_a_row_bitmap(Inde
             assert np.array_equal(g_ids[i], w_ids) and np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64))
 
 
+def test_filter_handle_is_resolved_once_and_follows_upserts_and_deletes(Index, small_table):
+    """`orx_filter_*`: same answers as the per-call filter; the device bitmap is rebuilt only when the id -> row
+    map has changed, and then denotes the live rows whose id is in the set."""
+    import outline_rag_b200 as orx
+    X, Q, _ = small_table
+    n = X.shape[0]
+    ids = _ids(n, 10)
+    rng = np.random.default_rng(4)
+    sel = np.sort(rng.choice(n, size=5000, replace=False))
+    few = sel[:30]
+    with Index("fp32") as ix, Index("fp32") as other:
+        ix.upsert(ids[:6000], X[:6000])
+        with ix.make_filter(ids[sel]) as big, ix.make_filter(ids[few]) as small:
+            def check(flt, rows_live):
+                got = ix.search_filtered(Q[:3], K, flt)
+                for i in range(3):
+                    w_ids, w_d = O.topk_exact(X[rows_live], ids[rows_live], Q[i], K, exhaustive=True)
+                    assert got[2][i] == len(w_d)
+                    assert np.array_equal(got[0][i, :len(w_d)], w_ids)
+                    assert np.array_equal(got[1][i, :len(w_d)].view(np.uint64), w_d.view(np.uint64))
+            live = sel[sel < 6000]                                  # only part of the set is in the table yet
+            assert len(live) < 4096                                 # ... so this is the list regime
+            check(big, live)
+            check(small, few[few < 6000])
+            ix.upsert(ids[6000:], X[6000:])                         # the rest arrives: bitmap regime from now on
+            launches0 = ix.stats()["scan_launches"]
+            check(big, sel)
+            check(big, sel)                                         # second use: nothing to resolve
+            assert ix.stats()["scan_launches"] == launches0 + 2
+            check(small, few)
+            ix.upsert(ids[sel[:5]], X[sel[:5]])                     # overwrite in place: same rows, same answers
+            check(big, sel)
+            assert ix.delete(ids[sel[100:900]]) == 800              # rows move; 4200 eligible rows remain
+            keep = np.ones(5000, bool)
+            keep[100:900] = False
+            check(big, sel[keep])
+            assert ix.delete(ids[sel[900:1200]]) == 300             # 3900 left: back to the list regime
+            keep[900:1200] = False
+            check(big, sel[keep])
+            with pytest.raises(orx.OrxValueError, match="another index"):
+                other.search_filtered(Q[:1], K, big)
+        with pytest.raises(orx.OrxValueError, match="closed"):
+            ix.search_filtered(Q[:1], K, big)
+
+
 def test_large_k_for_a_wider_reranker_feed(Index, small_table):
     """k up to 128 (SURVEY.md 8f-4): batches stay exact (fp32 scan per query), ties and short tables too;
     the sharded exchange chunks the batch so that a slot still fits."""
