@@ -186,6 +186,10 @@ int orx_import_rows(orx_index *idx, const orx_id *ids, const void *rows_raw, uin
  * idx == NULL opens a DRY RUN: framing and element checks on the host, nothing loaded, no GPU needed. */
 typedef struct orx_pgcopy orx_pgcopy;
 int orx_pgcopy_open(orx_index *idx, orx_pgcopy **out);
+/* Row-sharded cold start: every rank feeds the SAME stream to its own loader, which keeps
+ * only the rows with mix64(id) mod world == rank (the shard function of outline_rag_b200/sharded.py) --
+ * no data-path collective, like the sharded upsert.  rows_loaded then counts this rank's rows. */
+int orx_pgcopy_open_sharded(orx_index *idx, int world, int rank, orx_pgcopy **out);
 int orx_pgcopy_feed(orx_pgcopy *ld, const void *bytes, uint64_t n);
 int orx_pgcopy_close(orx_pgcopy *ld, uint64_t *rows_loaded, uint64_t *rows_null);
 

@@ -75,11 +75,21 @@ inline uint32_t be32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint3
 inline uint16_t be16(const uint8_t *p) { return (uint16_t)(((uint16_t)p[0] << 8) | p[1]); }
 inline uint64_t be64(const uint8_t *p) { return ((uint64_t)be32(p) << 32) | be32(p + 4); }
 
+// the row-shard function of outline_rag_b200/sharded.py:shard_of: mix64(hi * GOLD ^ lo) mod G
+inline uint32_t shard_of_id(uint64_t hi, uint64_t lo, uint32_t world) {
+    uint64_t z = hi * 0x9E3779B97F4A7C15ull ^ lo;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z % world);
+}
+
 }  // namespace
 
 struct orx_pgcopy {
     orx_index *ix = nullptr;          // null: dry run (framing + element check on the host, nothing loaded)
     int device = 0;                   // the index's GPU (kept here: freeing the loader must not touch the index)
+    uint32_t world = 1, rank = 0;     // row-sharded load: keep only the ids this rank owns (sharded.py shard_of)
     enum State { HEADER, EXTENSION, TUPLES, DONE, FAILED } state = HEADER;
     uint8_t *raw = nullptr;           // staging (pinned when loading): the bytes not yet flushed
     size_t fill = 0, pos = 0;         // bytes held / parsed
@@ -90,7 +100,7 @@ struct orx_pgcopy {
     uint8_t *d_raw = nullptr;
     uint64_t *d_offs = nullptr;
     float *d_vecs = nullptr;
-    uint64_t rows = 0, nulls = 0, bytes = 0;
+    uint64_t rows = 0, nulls = 0, foreign = 0, bytes = 0;
     int err = ORX_OK;
 };
 
@@ -253,11 +263,17 @@ int pg_parse(orx_pgcopy *ld) {
                     return pg_fail(ld, ORX_ERR_INVALID);
                 }
                 if (have < PG_TUPLE_MAX) return ORX_OK;
+                const orx_id id{be64(p + 6), be64(p + 14)};
+                if (ld->world > 1 && shard_of_id(id.hi, id.lo, ld->world) != ld->rank) {
+                    ld->foreign += 1;                                     // another rank's row: not staged
+                    ld->pos += PG_TUPLE_MAX;
+                    break;
+                }
                 if (!ld->ix) {
                     const int rc = pg_check_elements_host(ld, p + PG_TUPLE_HEAD + 4);
                     if (rc != ORX_OK) return rc;
                 }
-                ld->ids[ld->n_batch] = orx_id{be64(p + 6), be64(p + 14)};
+                ld->ids[ld->n_batch] = id;
                 ld->offs[ld->n_batch] = ld->pos + PG_TUPLE_HEAD + 4;
                 ld->n_batch += 1;
                 ld->pos += PG_TUPLE_MAX;
@@ -303,11 +319,16 @@ inline bool vector_isspace(char c) { return c == ' ' || c == '\t' || c == '\n' |
 
 extern "C" {
 
-int orx_pgcopy_open(orx_index *ix, orx_pgcopy **out) {
+int orx_pgcopy_open(orx_index *ix, orx_pgcopy **out) { return orx_pgcopy_open_sharded(ix, 1, 0, out); }
+
+int orx_pgcopy_open_sharded(orx_index *ix, int world, int rank, orx_pgcopy **out) {
     if (!out) return orx::set_error(ORX_ERR_INVALID, "out is null");
     *out = nullptr;
+    if (world < 1 || rank < 0 || rank >= world) return orx::set_error(ORX_ERR_INVALID, "bad world/rank %d/%d", rank, world);
     orx_pgcopy *ld = new orx_pgcopy();
     ld->ix = ix;
+    ld->world = (uint32_t)world;
+    ld->rank = (uint32_t)rank;
     if (ix) {
         int prev = -1;
         cudaGetDevice(&prev);

@@ -124,13 +124,15 @@ class PgCopyLoader:
 
     ``feed`` takes the stream in chunks of any size (bytes / bytearray / memoryview, e.g. what psycopg 3's
     ``async for data in copy`` yields); ``close`` flushes and returns ``(rows_loaded, rows_null)``.
-    ``index=None`` is a dry run that only validates the stream on the host (no GPU)."""
+    ``index=None`` is a dry run that only validates the stream on the host (no GPU).  ``world`` / ``rank``:
+    keep only the rows this rank owns under ``sharded.shard_of`` (every rank feeds the same stream)."""
 
-    def __init__(self, index: "Index | None" = None):
+    def __init__(self, index: "Index | None" = None, world: int = 1, rank: int = 0):
         self._ld = C.c_void_p()
         self._index = index          # keeps the table alive while the loader holds its handle
         self.result = None           # (rows_loaded, rows_null) once closed
-        check(lib.orx_pgcopy_open(index._h if index is not None else None, C.byref(self._ld)))
+        check(lib.orx_pgcopy_open_sharded(index._h if index is not None else None, int(world), int(rank),
+                                          C.byref(self._ld)))
 
     def feed(self, data) -> None:
         if not self._ld:
@@ -330,14 +332,14 @@ class Index:
                                          C.c_void_p(dist_out.data_ptr()), C.c_void_p(counts_out.data_ptr())))
 
     # -- cold start from Postgres
-    def pgcopy_loader(self) -> PgCopyLoader:
-        return PgCopyLoader(self)
+    def pgcopy_loader(self, world: int = 1, rank: int = 0) -> PgCopyLoader:
+        return PgCopyLoader(self, world, rank)
 
-    def load_pgcopy(self, chunks) -> tuple[int, int]:
+    def load_pgcopy(self, chunks, world: int = 1, rank: int = 0) -> tuple[int, int]:
         """Feed an iterable of COPY BINARY chunks (or one bytes object); -> (rows_loaded, rows_null)."""
         if isinstance(chunks, (bytes, bytearray, memoryview)):
             chunks = (chunks,)
-        ld = PgCopyLoader(self)
+        ld = PgCopyLoader(self, world, rank)
         with ld:
             for c in chunks:
                 ld.feed(c)

@@ -153,6 +153,12 @@ class ShardedIndex:
         sel = self._mine(ida)
         return self.local.delete(ida[sel]) if sel.size else 0
 
+    def load_pgcopy(self, chunks) -> tuple[int, int]:
+        """Cold start of a row-sharded table: every rank feeds the SAME `COPY ... (FORMAT binary)` stream;
+        the loader keeps the rows this rank owns (the C side applies `shard_of`).  No collective.
+        -> (rows loaded on this rank, rows with a NULL embedding in the whole stream)."""
+        return self.local.load_pgcopy(chunks, self.world, self.rank)
+
     # ------------------------------------------------------------------- reads
     def search(self, queries, k: int = 12):
         """Global top-k on every rank.  ``queries`` is identical on all ranks (CUDA tensor for the

@@ -112,3 +112,63 @@ def test_vectorstore_call_sequence_on_a_fake_index(small_table):
 
     asyncio.run(run())
     assert [op for op, _ in owner.log] == ["upsert", "upsert", "delete"]
+
+
+def test_async_cold_start_coalesces_driver_chunks_and_always_frees_the_loader():
+    """`aload_pgcopy`: psycopg yields tens of KB per chunk; the store hands the loader blocks of `feed_bytes`
+    (one worker-thread hop each), closes it at the end, and closes it too when the stream breaks."""
+    import outline_rag_b200 as orx
+
+    class FakeLoader:
+        def __init__(self):
+            self.blocks, self.closed = [], 0
+
+        def feed(self, data):
+            self.blocks.append(bytes(data))
+
+        def close(self):
+            self.closed += 1
+            return (sum(map(len, self.blocks)), 0)
+
+    class FakeIndex:
+        def __init__(self):
+            self.loaders = []
+
+        def pgcopy_loader(self):
+            self.loaders.append(FakeLoader())
+            return self.loaders[-1]
+
+    payload = bytes(range(256)) * 400                                       # 102400 bytes
+
+    async def chunks(fail_at=None):
+        for n, i in enumerate(range(0, len(payload), 1000)):
+            if fail_at is not None and n == fail_at:
+                raise ConnectionError("server closed the connection")
+            yield memoryview(payload)[i:i + 1000]
+
+    ix = FakeIndex()
+    store = orx.GpuVectorStore(ix, embedding_service=object())
+    assert asyncio.run(store.aload_pgcopy(chunks(), feed_bytes=30_000)) == (len(payload), 0)
+    ld = ix.loaders[0]
+    assert b"".join(ld.blocks) == payload and [len(b) for b in ld.blocks] == [30_000, 30_000, 30_000, 12_400]
+    assert ld.closed == 1
+    with pytest.raises(ConnectionError):
+        asyncio.run(store.aload_pgcopy(chunks(fail_at=50), feed_bytes=30_000))
+    assert ix.loaders[1].closed == 1 and len(ix.loaders[1].blocks) == 1      # 30 KB were fed before the break
+    assert "COPY (SELECT langchain_id, embedding FROM t " in store.COPY_SQL.format(table="t")
+
+
+def test_sharded_index_hands_its_rank_to_the_loader():
+    from outline_rag_b200.sharded import ShardedIndex
+
+    class Local:
+        def load_pgcopy(self, chunks, world, rank):
+            self.seen = (chunks, world, rank)
+            return (3, 1)
+
+        def merge_topk(self, *a):
+            raise AssertionError("not used")
+
+    loc = Local()
+    sh = ShardedIndex(local_index=loc)                                      # no process group: world 1, rank 0
+    assert sh.load_pgcopy(b"stream") == (3, 1) and loc.seen == (b"stream", 1, 0)

@@ -147,6 +147,33 @@ def test_dry_run_loader_accepts_eof_at_a_tuple_boundary_and_empty_tables():
     assert ld.close() == (0, 0)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_dry_run_keeps_exactly_the_rows_shard_of_assigns(world):
+    """Row-sharded cold start: every rank reads the whole stream and keeps mix64(id) mod G == rank -- the C
+    side must agree with `sharded.shard_of`, bit for bit, or rows would be lost / duplicated across GPUs."""
+    from outline_rag_b200.sharded import shard_of
+    rng = np.random.default_rng(world)
+    n = 600
+    ids = np.stack([rng.integers(0, 2**63, size=n).astype(np.uint64) * np.uint64(2) + np.uint64(1),
+                    rng.integers(0, 2**63, size=n).astype(np.uint64)], axis=1)
+    ids[:50, 0] = 0                                                # small ids (uuid.UUID(int=i)) too
+    X = rng.standard_normal((n, DIM)).astype(np.float32)
+    stream = W.copy_binary_stream(ids, X, null_rows=[7, 8])
+    live = np.ones(n, bool)
+    live[[7, 8]] = False
+    owner = shard_of(ids, world)
+    total = 0
+    for rank in range(world):
+        ld = orx.PgCopyLoader(None, world, rank)
+        _feed_all(ld, stream, 50_000)
+        rows, nulls = ld.close()
+        assert rows == int(((owner == rank) & live).sum()) and nulls == 2
+        total += rows
+    assert total == n - 2
+    with pytest.raises(orx.OrxValueError, match="bad world/rank"):
+        orx.PgCopyLoader(None, 2, 2)
+
+
 def _corrupt(stream: bytes, at: int, repl: bytes) -> bytes:
     return stream[:at] + repl + stream[at + len(repl):]
 
@@ -260,6 +287,31 @@ def test_pgcopy_load_rejects_a_nan_batch_and_keeps_earlier_batches():
         assert ld.result == (16384, 0) and len(ix) == 16384        # the batch before the bad one stays loaded
     with orx.Index("fp32") as ix, pytest.raises(orx.OrxValueError, match="expected 1024 dimensions"):
         ix.load_pgcopy(W.copy_binary_stream(ids[:2], X[:2, :512]))
+
+
+@pytest.mark.gpu
+def test_sharded_pgcopy_load_partitions_the_stream_without_loss():
+    from outline_rag_b200.sharded import shard_of
+    n = 900
+    ids, X = _rows(n, seed=13)
+    stream = W.copy_binary_stream(ids, X, null_rows=[5])
+    owner = shard_of(ids, 2)
+    owner[5] = -1
+    with orx.Index("fp32") as a, orx.Index("fp32") as b:
+        ra = a.load_pgcopy([stream[:300_000], stream[300_000:]], world=2, rank=0)
+        rb = b.load_pgcopy(stream, world=2, rank=1)
+        assert ra == (int((owner == 0).sum()), 1) and rb == (int((owner == 1).sum()), 1)
+        for ix, r in ((a, 0), (b, 1)):
+            got, found = ix.fetch(ids)
+            assert np.array_equal(found, owner == r)
+            assert np.array_equal(got[found].view(np.uint32), X[owner == r].view(np.uint32))
+        # the two shards merge to the answer of one table holding every row
+        q = X[40] + 0.05 * X[41]
+        pa, pb = a.search(q, 12), b.search(q, 12)
+        merged = a.merge_topk(np.stack([pa[0], pb[0]]), np.stack([pa[1], pb[1]]), np.stack([pa[2], pb[2]]), 12)
+        keep = owner >= 0
+        w_ids, w_d = O.topk_exact(X[keep], ids[keep], q, 12)
+        assert np.array_equal(merged[0][0], w_ids) and np.array_equal(merged[1][0].view(np.uint64), w_d.view(np.uint64))
 
 
 @pytest.mark.gpu
