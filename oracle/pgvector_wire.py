@@ -132,6 +132,8 @@ def copy_binary_parse(stream: bytes, expected_dim: int = 1024):
             if ln == -1:
                 fields.append(None)
                 continue
+            if ln < 0:
+                raise WireError("format", "invalid field size")
             if len(stream) - p < ln:
                 raise WireError("format", "unexpected EOF in COPY data")
             fields.append(stream[p:p + ln])

@@ -124,6 +124,25 @@ def test_parse_vector_text_langchain_serialisation(seed):
     assert np.array_equal(got.view(np.uint32), W.vector_in(text).view(np.uint32))
 
 
+@settings(max_examples=300, deadline=None)
+@given(st.text(alphabet="[], \t0123456789.eE+-nNaAiIfF", min_size=0, max_size=24), st.booleans())
+def test_fuzzed_vector_text_is_accepted_or_rejected_exactly_like_the_oracle(body, wrap):
+    """Random token soup (decimal syntax only: hex floats, which strtof also takes, are outside the oracle):
+    same accept / reject decision as the restatement of vector_in, same fp32 bits when accepted."""
+    text = f"[{body}]" if wrap else body
+    try:
+        want = W.vector_in(text)
+    except W.WireError:
+        want = None
+    try:
+        got = orx.parse_vector_text(text, dim=want.shape[0] if want is not None else 3)
+    except orx.OrxValueError:
+        got = None
+    assert (got is None) == (want is None), (text, want, got)
+    if want is not None:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), text
+
+
 # ------------------------------------------------------------------------------- COPY framing, dry run (host)
 @pytest.mark.parametrize("step", [1, 7, 4126, 4127, 65536, 1 << 30])
 def test_dry_run_loader_counts_rows_for_any_chunking(step):
@@ -203,6 +222,52 @@ def test_dry_run_loader_rejects_what_postgres_and_pgvector_reject(name, mutate, 
     assert ei.value.code == code
     with pytest.raises(W.WireError):
         W.copy_binary_parse(bad)
+
+
+@settings(max_examples=150, deadline=None)
+@given(st.integers(0, 2**31 - 1))
+def test_fuzzed_streams_are_accepted_or_rejected_exactly_like_the_oracle(seed):
+    """Random byte mutations, truncations and splices of a valid stream, fed in random chunk sizes: the C
+    walker never crashes, accepts exactly what the strict Python restatement accepts, and counts the same rows."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 5))
+    ids, X = _rows(n, seed=seed % 1000)
+    nulls = [int(i) for i in np.nonzero(rng.random(n) < 0.3)[0]]
+    s = bytearray(W.copy_binary_stream(ids, X, null_rows=nulls, header_extension=bytes(int(rng.integers(0, 6))),
+                                       trailer=bool(rng.random() < 0.8)))
+    kind = int(rng.integers(0, 5))
+    if kind == 0:                                                   # corrupt framing bytes near the front
+        for _ in range(int(rng.integers(1, 4))):
+            s[int(rng.integers(0, min(len(s), 80)))] = int(rng.integers(0, 256))
+    elif kind == 1:                                                 # corrupt bytes anywhere (mostly payload)
+        for _ in range(int(rng.integers(1, 4))):
+            s[int(rng.integers(0, len(s)))] = int(rng.integers(0, 256))
+    elif kind == 2:                                                 # truncate
+        del s[int(rng.integers(0, len(s))):]
+    elif kind == 3:                                                 # splice garbage in / append after the trailer
+        at = int(rng.integers(0, len(s) + 1))
+        s[at:at] = rng.integers(0, 256, size=int(rng.integers(1, 9)), dtype=np.uint8).tobytes()
+    s = bytes(s)
+    try:
+        _, Xo, nn = W.copy_binary_parse(s)
+        want = (Xo.shape[0], nn)
+    except W.WireError:
+        want = None
+    got = None
+    ld = orx.PgCopyLoader(None)
+    try:
+        p = 0
+        while p < len(s):
+            step = int(rng.integers(1, 6000))
+            ld.feed(s[p:p + step])
+            p += step
+        got = ld.close()
+    except orx.OrxError:
+        try:
+            ld.close()
+        except orx.OrxError:
+            pass
+    assert got == want, (kind, want, got)
 
 
 def test_loader_fails_for_good_after_an_error():
