@@ -43,15 +43,24 @@ DEFAULT_METADATA_COLUMNS = ["source_id", "title", "outline_updated_at_str", "url
 
 
 class MemoryDocStore:
-    """``langchain_id -> (content, metadata)``: what stays in Postgres in production
-    (columns ``content`` + the 4 metadata columns, reference app/database.py:118-131)."""
+    """``langchain_id -> (content, metadata[, embedding])``: what stays in Postgres in production
+    (columns ``content``, ``embedding`` + the 4 metadata columns, reference app/database.py:118-131).
+    Postgres remains the source of truth for the embeddings too (`stores_embeddings`): the device table is
+    rebuilt from it on restart (`copy_binary` = what `GpuVectorStore.COPY_SQL` streams)."""
+
+    stores_embeddings = True
 
     def __init__(self):
         self._rows: dict[str, tuple[str, dict]] = {}
+        self._emb: dict[str, np.ndarray] = {}
 
-    def put_many(self, ids: Sequence[str], contents: Sequence[str], metadatas: Sequence[dict]) -> None:
-        for i, c, m in zip(ids, contents, metadatas):
+    def put_many(self, ids: Sequence[str], contents: Sequence[str], metadatas: Sequence[dict], embeddings=None) -> None:
+        for n, (i, c, m) in enumerate(zip(ids, contents, metadatas)):
             self._rows[i] = (c, dict(m))
+            if embeddings is not None:
+                self._emb[i] = np.array(embeddings[n], dtype=np.float32)
+            else:
+                self._emb.pop(i, None)                       # INSERT ... DO UPDATE without a vector: NULL
 
     def get_many(self, ids: Sequence[str]) -> list[Optional[tuple[str, dict]]]:
         return [self._rows.get(i) for i in ids]
@@ -59,6 +68,26 @@ class MemoryDocStore:
     def delete_many(self, ids: Iterable[str]) -> None:
         for i in ids:
             self._rows.pop(i, None)
+            self._emb.pop(i, None)
+
+    def copy_binary(self, rows_per_chunk: int = 256):
+        """Yield what `COPY (SELECT langchain_id, embedding FROM langchain_pg_embedding) TO STDOUT (FORMAT
+        binary)` streams for this store (PostgreSQL COPY binary format; pgvector's vector_send image; a row
+        without an embedding is a NULL field), in chunks -- the stand-in for psycopg's `cursor.copy()`."""
+        import struct
+        yield b"PGCOPY\n\xff\r\n\x00" + bytes(8)
+        buf = []
+        for i in self._rows:
+            buf.append(struct.pack(">hi", 2, 16) + uuid.UUID(i).bytes)
+            e = self._emb.get(i)
+            if e is None:
+                buf.append(struct.pack(">i", -1))
+            else:
+                buf.append(struct.pack(">ihh", 4 + 4 * e.shape[0], e.shape[0], 0) + e.astype(">f4").tobytes())
+            if len(buf) >= 2 * rows_per_chunk:
+                yield b"".join(buf)
+                buf = []
+        yield b"".join(buf) + b"\xff\xff"
 
     def ids_for_filter(self, flt: dict) -> list[str]:
         """Resolve a metadata predicate to chunk ids -- `SELECT langchain_id ... WHERE <filter>` in
@@ -169,7 +198,10 @@ class GpuVectorStore:
         if n == 0:
             return []
         self.index.upsert(ids, emb)                      # raises on wrong dim / NaN, nothing stored
-        self.doc_store.put_many(ids, list(texts), metadatas)
+        if getattr(self.doc_store, "stores_embeddings", False):
+            self.doc_store.put_many(ids, list(texts), metadatas, embeddings=emb)     # durable copy (cold start)
+        else:
+            self.doc_store.put_many(ids, list(texts), metadatas)
         return ids
 
     async def aadd_embeddings(self, texts, embeddings, metadatas=None, ids=None) -> list[str]:

@@ -172,3 +172,27 @@ def test_sharded_index_hands_its_rank_to_the_loader():
     loc = Local()
     sh = ShardedIndex(local_index=loc)                                      # no process group: world 1, rank 0
     assert sh.load_pgcopy(b"stream") == (3, 1) and loc.seen == (b"stream", 1, 0)
+
+
+def test_memory_doc_store_streams_its_embeddings_in_copy_binary_format():
+    """The in-memory stand-in for `langchain_pg_embedding` emits what the COPY statement of the cold start
+    streams: the oracle decodes it back to the stored rows, NULL embeddings included."""
+    from oracle import pgvector_wire as W
+    import outline_rag_b200 as orx
+    st = orx.MemoryDocStore()
+    rng = np.random.default_rng(1)
+    X = rng.standard_normal((300, 1024)).astype(np.float32)
+    ids = [str(uuid.UUID(int=3 * i + 1)) for i in range(300)]
+    st.put_many(ids, ["c"] * 300, [{"source_id": "d"}] * 300, embeddings=X)
+    st.put_many([str(uuid.UUID(int=2))], ["no vector yet"], [{}])                # NULL embedding
+    st.delete_many(ids[10:20])
+    chunks = list(st.copy_binary(rows_per_chunk=32))
+    assert len(chunks) > 5 and max(map(len, chunks)) < 40 * 4200
+    got_ids, got_X, n_null = W.copy_binary_parse(b"".join(chunks))
+    keep = [i for i in range(300) if not 10 <= i < 20]
+    assert n_null == 1 and O.ids_to_ints(got_ids) == [3 * i + 1 for i in keep]
+    assert np.array_equal(got_X.view(np.uint32), X[keep].view(np.uint32))
+    ld = orx.PgCopyLoader(None)                                                  # and the C walker agrees
+    for c in chunks:
+        ld.feed(c)
+    assert ld.close() == (290, 1)

@@ -116,3 +116,36 @@ def test_metadata_filter_restricts_the_candidates(synth100k):
         assert [d.id for d, _ in got] == [str(uuid.UUID(int=v)) for v in O.ids_to_ints(w_ids)]
         assert [s for _, s in got] == w_d.tolist()
     store.index.close()
+
+
+def test_restart_rebuilds_the_device_table_from_the_doc_store(synth100k):
+    """Postgres stays the source of truth: a new process streams `COPY (SELECT langchain_id, embedding ...)` from
+    it (here: the in-memory stand-in's `copy_binary`) and answers exactly like the process that was stopped."""
+    import uuid
+    import outline_rag_b200 as orx
+    n = 500
+    emb = FakeBgeM3(synth100k, n)
+
+    async def run():
+        first = await orx.GpuVectorStore.create(None, emb)
+        docs = [orx.Document(page_content=f"row:{i}", metadata={"source_id": f"doc{i // 20}"}, id=str(uuid.UUID(int=i + 1)))
+                for i in range(n)]
+        await first.aadd_documents(docs)
+        assert await first.adelete(ids=[d.id for d in docs[40:60]]) is True
+        before = [await first.asimilarity_search_with_score(f"q:{j}", k=orx.TOP_K) for j in range(4)]
+        durable = first.doc_store                                  # survives the "restart"
+        first.index.close()
+
+        second = await orx.GpuVectorStore.create(None, emb, doc_store=durable)
+
+        async def copy_stream():
+            for chunk in durable.copy_binary(rows_per_chunk=64):
+                yield chunk
+
+        assert await second.aload_pgcopy(copy_stream(), feed_bytes=1 << 20) == (n - 20, 0)
+        after = [await second.asimilarity_search_with_score(f"q:{j}", k=orx.TOP_K) for j in range(4)]
+        for b, a in zip(before, after):
+            assert [(d.id, d.page_content, s) for d, s in b] == [(d.id, d.page_content, s) for d, s in a]
+        second.index.close()
+
+    asyncio.run(run())
