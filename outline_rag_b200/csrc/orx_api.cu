@@ -1152,15 +1152,21 @@ int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids,
     }
     if (in_dev || out_dev) return fail(ORX_ERR_INVALID, "merge inputs and outputs must live on the same side");
     // host buffers: stage through device scratch (the merge itself always runs on the GPU)
-    orx_id *d_ids = nullptr, *d_oids = nullptr;
-    double *d_dist = nullptr, *d_odist = nullptr;
-    int *d_cnt = nullptr, *d_ocnt = nullptr;
-    CK(cudaMalloc(&d_ids, nin * sizeof(orx_id)));
-    CK(cudaMalloc(&d_dist, nin * sizeof(double)));
-    CK(cudaMalloc(&d_cnt, (size_t)n_lists * nq * sizeof(int)));
-    CK(cudaMalloc(&d_oids, nout * sizeof(orx_id)));
-    CK(cudaMalloc(&d_odist, nout * sizeof(double)));
-    CK(cudaMalloc(&d_ocnt, nq * sizeof(int)));
+    struct Scratch {                       // one allocation, released on every exit path
+        char *p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } scratch;
+    auto up16 = [](size_t b) { return (b + 15) & ~(size_t)15; };
+    const size_t b_ids = nin * sizeof(orx_id), b_dist = up16(nin * sizeof(double));
+    const size_t b_cnt = up16((size_t)n_lists * nq * sizeof(int));
+    const size_t b_oids = nout * sizeof(orx_id), b_odist = up16(nout * sizeof(double)), b_ocnt = up16(nq * sizeof(int));
+    CK(cudaMalloc(reinterpret_cast<void **>(&scratch.p), b_ids + b_dist + b_cnt + b_oids + b_odist + b_ocnt));
+    orx_id *d_ids = reinterpret_cast<orx_id *>(scratch.p);
+    double *d_dist = reinterpret_cast<double *>(scratch.p + b_ids);
+    int *d_cnt = reinterpret_cast<int *>(scratch.p + b_ids + b_dist);
+    orx_id *d_oids = reinterpret_cast<orx_id *>(scratch.p + b_ids + b_dist + b_cnt);
+    double *d_odist = reinterpret_cast<double *>(scratch.p + b_ids + b_dist + b_cnt + b_oids);
+    int *d_ocnt = reinterpret_cast<int *>(scratch.p + b_ids + b_dist + b_cnt + b_oids + b_odist);
     CK(cudaMemcpyAsync(d_ids, ids, nin * sizeof(orx_id), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_dist, dist, nin * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(d_cnt, counts, (size_t)n_lists * nq * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -1170,7 +1176,6 @@ int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids,
     CK(cudaMemcpyAsync(out_dist, d_odist, nout * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(out_counts, d_ocnt, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    cudaFree(d_ids); cudaFree(d_dist); cudaFree(d_cnt); cudaFree(d_oids); cudaFree(d_odist); cudaFree(d_ocnt);
     CK(cudaGetLastError());
     return ORX_OK;
 }
