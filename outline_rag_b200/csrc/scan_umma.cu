@@ -135,21 +135,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// ORX_EPI_LDS=1 (experimental build, `make variant NAME=lds DEFS=-DORX_EPI_LDS=1`): the epilogue's staged 1/|x|
-// values go through explicit shared-space instructions.  The default build reaches them through a generic pointer
-// (LD.E.128 / ST.E in the SASS); to be A/B-measured before it becomes the default.
-#ifndef ORX_EPI_LDS
-#define ORX_EPI_LDS 0
-#endif
-__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
-    float4 r;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
-    return r;
-}
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-
 // ---- CTA-pair (cta_group::2) variants
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -287,11 +272,7 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
         for (int h = 0; h < 2; ++h) {
             const float s = sc_next[h];
             special |= !(fabsf(s) < __int_as_float(0x7f800000));      // inf or NaN
-#if ORX_EPI_LDS
-            sts_f32(smem_u32(sc + et + 128 * h), s);
-#else
             sc[et + 128 * h] = s;
-#endif
             const uint32_t rn = n0 + (uint32_t)n_slots * TILE_N + et + 128 * h;
             sc_next[h] = (t + n_slots < n_tiles && rn < n_rows) ? __ldg(scale + rn) : __int_as_float(0x7fc00000);
         }
@@ -312,20 +293,12 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
-#if ORX_EPI_LDS
-            const uint32_t sc4_addr = smem_u32(sc + c * 32);
-#else
             const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c * 32);
-#endif
             float s[32];
             float mx = __int_as_float(0xff800000);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-#if ORX_EPI_LDS
-                const float4 f = lds_f4(sc4_addr + 16 * j4);
-#else
                 const float4 f = sc4[j4];
-#endif
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * f.x;
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
                 s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
