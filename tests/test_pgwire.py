@@ -404,3 +404,20 @@ def test_vectorstore_cold_start_from_an_async_copy_stream():
         store.index.close()
 
     asyncio.run(run())
+
+
+# ------------------------------------------------------------------------------- host-side encoder
+def test_encoder_emits_exactly_the_oracles_stream():
+    ids, X = _rows(37, seed=6)
+    assert orx.encode_copy_binary(ids, X) == W.copy_binary_stream(ids, X)
+    from outline_rag_b200.pgwire import COPY_HEADER, COPY_TRAILER, encode_tuples
+    parts = COPY_HEADER + encode_tuples(ids[:20], X[:20]) + encode_tuples(ids[20:], X[20:]) + COPY_TRAILER
+    assert parts == W.copy_binary_stream(ids, X)
+    import uuid
+    as_strings = [str(uuid.UUID(int=(int(h) << 64) | int(l))) for h, l in ids]
+    assert orx.encode_copy_binary(as_strings, X.tolist()) == W.copy_binary_stream(ids, X)
+    ld = orx.PgCopyLoader(None)
+    ld.feed(orx.encode_copy_binary(ids, X))
+    assert ld.close() == (37, 0)
+    with pytest.raises(ValueError):
+        orx.encode_copy_binary(ids[:3], X)

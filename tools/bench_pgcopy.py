@@ -13,18 +13,12 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-TUPLE = np.dtype([("nf", ">i2"), ("l1", ">i4"), ("id", ">u8", (2,)), ("l2", ">i4"), ("dim", ">i2"), ("unused", ">i2"),
-                  ("v", ">f4", (1024,))])
-
-
 def make_stream(n: int, seed: int = 7) -> bytes:
-    assert TUPLE.itemsize == 4126
+    from outline_rag_b200.pgwire import encode_copy_binary
     rng = np.random.default_rng(seed)
-    t = np.zeros(n, TUPLE)
-    t["nf"], t["l1"], t["l2"], t["dim"] = 2, 16, 4100, 1024
-    t["id"][:, 1] = np.arange(1, n + 1, dtype=np.uint64)
-    t["v"] = rng.standard_normal((n, 1024), dtype=np.float32)
-    return b"PGCOPY\n\xff\r\n\x00" + bytes(8) + t.tobytes() + b"\xff\xff"
+    ids = np.zeros((n, 2), np.uint64)
+    ids[:, 1] = np.arange(1, n + 1, dtype=np.uint64)
+    return encode_copy_binary(ids, rng.standard_normal((n, 1024), dtype=np.float32))
 
 
 def main():
@@ -58,7 +52,8 @@ def main():
         best = dt if best is None else min(best, dt)
     # the same decode on the host: framing is fixed-stride here, so NumPy's byte swap is the whole job
     t0 = time.perf_counter()
-    t = np.frombuffer(stream, TUPLE, count=a.rows, offset=19)
+    from outline_rag_b200.pgwire import tuple_dtype
+    t = np.frombuffer(stream, tuple_dtype(1024), count=a.rows, offset=19)
     X = t["v"].astype(np.float32)
     ids_h = t["id"].astype(np.uint64)
     cpu = time.perf_counter() - t0
