@@ -196,3 +196,45 @@ def test_memory_doc_store_streams_its_embeddings_in_copy_binary_format():
     for c in chunks:
         ld.feed(c)
     assert ld.close() == (290, 1)
+
+
+def test_prepared_filter_skips_the_doc_store_lookup(small_table):
+    """`prepare_filter` resolves the metadata predicate once; later searches hand the device-resident handle
+    straight to the index (no doc-store query, no id -> row resolution per call)."""
+    import outline_rag_b200 as orx
+    from outline_rag_b200.engine import Filter
+    X, _, _ = small_table
+
+    class Handle(Filter):                                   # a Filter without the C object behind it
+        def __init__(self, ids):
+            self.ids = ids
+
+        def close(self):
+            pass
+
+    class Ix(FakeStoreIndex):
+        def make_filter(self, ids):
+            self.made = getattr(self, "made", 0) + 1
+            return Handle(list(ids))
+
+        def search_filtered(self, q, k, allow):
+            self.last_allow = allow
+            return super().search_filtered(q, k, allow.ids if isinstance(allow, Handle) else allow)
+
+    owner = Ix(np.zeros((0, 1024), np.float32), np.zeros((0, 2), np.uint64))
+    store = orx.GpuVectorStore(owner, FakeEmb(X))
+    docs = [orx.Document(page_content=str(i), metadata={"source_id": f"d{i // 10}"}, id=str(uuid.UUID(int=i + 1)))
+            for i in range(50)]
+    asyncio.run(store.aadd_documents(docs))
+    flt = store.prepare_filter({"source_id": {"$in": ["d1", "d3"]}})
+    assert owner.made == 1 and len(flt.ids) == 20
+    lookups = []
+    real = store.doc_store.ids_for_filter
+    store.doc_store.ids_for_filter = lambda f: lookups.append(f) or real(f)
+    for probe in (12, 33):
+        hits = store.similarity_search_with_score_by_vector(X[probe], 5, filter=flt)
+        assert owner.last_allow is flt and hits[0][0].page_content == str(probe)
+        assert all(d.metadata["source_id"] in ("d1", "d3") for d, _ in hits)
+    assert lookups == []                                    # the prepared handle bypassed the doc store
+    store.similarity_search_with_score_by_vector(X[12], 5, filter={"source_id": "d1"})
+    assert lookups == [{"source_id": "d1"}]
