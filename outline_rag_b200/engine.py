@@ -137,6 +137,8 @@ class PgCopyLoader:
     def feed(self, data) -> None:
         if not self._ld:
             raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "loader is closed")
+        if self._index is not None and not self._index._h:
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "the index of this loader was closed")
         a = np.frombuffer(data, dtype=np.uint8)          # zero-copy view of any contiguous buffer
         if a.size:
             check(lib.orx_pgcopy_feed(self._ld, C.c_void_p(a.ctypes.data), a.size))
@@ -146,6 +148,8 @@ class PgCopyLoader:
             return (0, 0)
         rows, nulls = C.c_uint64(0), C.c_uint64(0)
         ld, self._ld = self._ld, C.c_void_p()
+        if self._index is not None and not self._index._h:
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "the index of this loader was closed before the loader")
         rc = lib.orx_pgcopy_close(ld, C.byref(rows), C.byref(nulls))
         self.result = (int(rows.value), int(nulls.value))
         check(rc)
