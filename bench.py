@@ -172,6 +172,7 @@ def time_cpu_replica(rows_full: int, sample_rows: int, batch: int, n_queries: in
         if time.perf_counter() > t_end and i >= 3:
             break
     per_query_s = float(np.median(lat)) * (rows_full / sample_rows)
+    pgv = time_pgvector_loop(X, Q, rows_full, n_cores)
     try:
         from threadpoolctl import threadpool_info
         thr = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
@@ -182,7 +183,39 @@ def time_cpu_replica(rows_full: int, sample_rows: int, batch: int, n_queries: in
             "sample": f"NumPy replica (OpenBLAS sgemv+argpartition+lexsort, precomputed row norms) on the first "
                       f"{sample_rows} rows, {len(lat)} single queries, median latency scaled x{rows_full / sample_rows:.0f} "
                       f"to {rows_full} rows",
-            "p50_ms_sample": float(np.median(lat)) * 1e3, "host_cpus": os.cpu_count()}
+            "p50_ms_sample": float(np.median(lat)) * 1e3, "host_cpus": os.cpu_count(), "pgvector_loop": pgv}
+
+
+def time_pgvector_loop(X, Q, rows_full: int, n_cores: int, reps: int = 3):
+    """The C restatement of pgvector's own scan loop (oracle/pgv_cosine.c: per-row cosine_distance with float
+    accumulators + bounded heap, compiled with pgvector's flags): one thread = one Postgres backend running
+    the sequential scan, all threads = a parallel seq scan.  Scaled to the full table by rows.  Reported next
+    to the NumPy arm, which is the faster of the two CPU statements and therefore the one compared against."""
+    import ctypes
+    path = os.path.join(ROOT, "oracle", "libpgv_cosine.so")
+    try:
+        if not os.path.exists(path):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+        lib = ctypes.CDLL(path)
+    except Exception as e:      # noqa: BLE001 -- an optional extra of the CPU arm
+        return {"unavailable": str(e)[:120]}
+    lib.pgv_scan_topk_mt.restype = ctypes.c_int
+    lib.pgv_scan_topk_mt.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                     ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    n = X.shape[0]
+    rows = np.zeros(K, np.int64)
+    dist = np.zeros(K, np.float64)
+    out = {}
+    for name, threads in (("one_backend", 1), ("parallel_seq_scan", n_cores)):
+        lat = []
+        for r in range(reps):
+            q = np.ascontiguousarray(Q[r % Q.shape[0]], np.float32)
+            t0 = time.perf_counter()
+            lib.pgv_scan_topk_mt(X.ctypes.data, n, DIM, q.ctypes.data, K, threads, rows.ctypes.data, dist.ctypes.data)
+            lat.append(time.perf_counter() - t0)
+        s_full = float(np.median(lat)) * (rows_full / n)
+        out[name] = {"threads": threads, "queries_per_s": 1.0 / s_full, "p50_ms_sample": float(np.median(lat)) * 1e3}
+    return out
 
 
 def run_reference(a):

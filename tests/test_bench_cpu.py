@@ -18,6 +18,9 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
     assert "50000x1024" in line["config"]["workload"]
+    pgv = line["cpu_baseline"]["pgvector_loop"]                  # the C restatement of pgvector's scan loop, timed too
+    assert pgv["one_backend"]["threads"] == 1 and pgv["one_backend"]["queries_per_s"] > 0
+    assert pgv["parallel_seq_scan"]["queries_per_s"] > 0
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():
