@@ -172,7 +172,10 @@ def time_cpu_replica(rows_full: int, sample_rows: int, batch: int, n_queries: in
         if time.perf_counter() > t_end and i >= 3:
             break
     per_query_s = float(np.median(lat)) * (rows_full / sample_rows)
-    pgv = time_pgvector_loop(X, Q, rows_full, n_cores)
+    try:
+        pgv = time_pgvector_loop(np.ascontiguousarray(X, np.float32), Q, rows_full, n_cores)
+    except Exception as e:      # noqa: BLE001 -- an optional extra must never cost the bench line
+        pgv = {"unavailable": str(e)[:120]}
     try:
         from threadpoolctl import threadpool_info
         thr = max([p.get("num_threads", 1) for p in threadpool_info() if p.get("user_api") == "blas"] or [1])
