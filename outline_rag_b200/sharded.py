@@ -188,12 +188,30 @@ class ShardedIndex:
         ids, dist_, cnt = self.local.search(queries, k)
         if self.world == 1:
             return ids, dist_, cnt
+        return self._gather_merge(ids, dist_, cnt, k)
+
+    def search_filtered(self, queries, k: int, allow_ids):
+        """COLLECTIVE filtered search (`WHERE langchain_id IN (...)`, see Index.search_filtered): every rank
+        resolves the predicate against its own shard -- it is handed only the ids it owns -- and the k
+        candidates per rank are exchanged and merged like `search`.  Host (NumPy) queries and results."""
+        ida = ids_to_array(allow_ids)
+        if self.world > 1:
+            ida = ida[self._mine(ida)]
+        ids, dist_, cnt = self.local.search_filtered(queries, k, ida)
+        if self.world == 1:
+            return ids, dist_, cnt
+        return self._gather_merge(ids, dist_, cnt, k)
+
+    def _gather_merge(self, ids, dist_, cnt, k: int):
+        """One all_gather of the packed per-rank results + the merge; NumPy in -> NumPy out."""
         as_numpy = not isinstance(ids, torch.Tensor)
         if as_numpy:
             ids = torch.from_numpy(np.ascontiguousarray(ids).view(np.int64))
             dist_ = torch.from_numpy(np.ascontiguousarray(dist_))
             cnt = torch.from_numpy(np.ascontiguousarray(cnt))
         block = pack_results(ids, dist_, cnt)
+        if not block.is_cuda and dist.get_backend(self.group) == "nccl":
+            block = block.cuda(getattr(self.local, "device", None))      # NCCL moves device buffers only
         nq = block.shape[0]
         gathered = torch.empty((self.world * nq, block.shape[1]), dtype=torch.int64, device=block.device)
         dist.all_gather_into_tensor(gathered, block, group=self.group)   # rank-major concatenation
@@ -201,7 +219,7 @@ class ShardedIndex:
         self.gather_launches += 1
         g_ids, g_dist, g_cnt = unpack_results(gathered, k)
         if as_numpy:
-            return self._merge(g_ids.numpy().view(np.uint64), g_dist.numpy(), g_cnt.numpy(), k)
+            return self._merge(g_ids.cpu().numpy().view(np.uint64), g_dist.cpu().numpy(), g_cnt.cpu().numpy(), k)
         return self._merge(g_ids, g_dist, g_cnt, k)
 
 

@@ -48,6 +48,15 @@ class OracleLocalIndex:
         return ids, d, cnt
 
 
+    def search_filtered(self, queries, k, allow):
+        ok = {tuple(map(int, r)) for r in np.asarray(allow, np.uint64).reshape(-1, 2)}
+        keep = np.array([tuple(map(int, r)) in ok for r in self.ids], bool)
+        sub = OracleLocalIndex()
+        sub.ids, sub.X = self.ids[keep], self.X[keep]
+        self.last_allow_size = len(ok)
+        return sub.search(np.asarray(queries, np.float32), k)
+
+
 def oracle_merge(g_ids, g_dist, g_cnt, k):
     from oracle import cosine_topk as O
     n_lists, nq = g_dist.shape[:2]
@@ -85,8 +94,12 @@ def _worker(rank, world, port, out_dir):
         sh.delete(gone)
         assert sh.global_size() == n - 40
         got2 = sh.search(Q, k)
+        # the WHERE-clause search: every rank is handed only the allowed ids it owns
+        allow = ids[200:260]
+        got3 = sh.search_filtered(Q, k, allow)
+        assert sh.local.last_allow_size == int((shard_of(allow, world) == rank).sum())
         np.savez(os.path.join(out_dir, f"r{rank}.npz"), ids=got[0], d=got[1], c=got[2], ids2=got2[0],
-                 d2=got2[1], c2=got2[2], kept=kept)
+                 d2=got2[1], c2=got2[2], ids3=got3[0], d3=got3[1], c3=got3[2], kept=kept)
     finally:
         dist.destroy_process_group()
 
@@ -121,6 +134,9 @@ def test_two_rank_sharded_search_equals_single_table(tmp_path):
             assert np.array_equal(rr["ids"][qi], w_ids) and np.array_equal(rr["d"][qi], w_d)
             assert rr["c"][qi] == k
             assert np.array_equal(rr["ids2"][qi], w2_ids) and np.array_equal(rr["d2"][qi], w2_d)
+        w3_ids, w3_d = O.topk_exact(X[200:260], ids[200:260], Q[qi], k, exhaustive=True)
+        for rr in r:
+            assert rr["c3"][qi] == k and np.array_equal(rr["ids3"][qi], w3_ids) and np.array_equal(rr["d3"][qi], w3_d)
 
 
 def test_pack_unpack_roundtrip():

@@ -74,6 +74,11 @@ def _worker(rank, world, port, out_dir):
                 got = sh.search(qd[:nq], K)
                 res[f"{mode}_ids_{nq}"] = got[0].cpu().numpy().view(np.uint64).copy()
                 res[f"{mode}_d_{nq}"] = got[1].cpu().numpy().copy()
+            if mode == "nccl":
+                # the WHERE-clause search across shards (each rank resolves the ids it owns; all_gather + merge)
+                f = sh.search_filtered(Q[:3], K, ids[5000:15000])
+                res["filtered_ids"] = f[0]
+                res["filtered_d"] = f[1]
             if mode == "p2p":
                 h = sh.search(Q[:3], K)                       # host buffers through the C-ABI
                 res["p2p_host_ids"] = h[0]
@@ -115,3 +120,7 @@ def test_two_gpus_p2p_and_nccl_equal_the_oracle(tmp_path):
             if qi < 4:
                 w2, _ = O.topk_exact(X[keep], ids[keep], Q[qi], K)
                 assert np.array_equal(rr["p2p_after_delete_ids"][qi], w2)
+            if qi < 3:
+                w3, w3d = O.topk_exact(X[5000:15000], ids[5000:15000], Q[qi], K)
+                assert np.array_equal(rr["filtered_ids"][qi], w3)
+                assert np.array_equal(rr["filtered_d"][qi].view(np.uint64), w3d.view(np.uint64))
