@@ -9,13 +9,14 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, ORX_DIM, ORX_MAX_K, OrxError, OrxValue
 from .batcher import QueryBatcher
 from .daemon import IndexServer, RemoteIndex, serve_in_thread
 from .engine import Filter, Index, PgCopyLoader, parse_vector_text, ids_to_array, ids_to_ints, ids_to_uuid_strs, synth_rows_device
+from .docstore_sql import SqlDocStore, vector_to_text
 from .pgwire import encode_copy_binary
 from .vectorstore import Document, GpuRetriever, GpuVectorStore, MemoryDocStore
 
 TOP_K = 12               # reference app/config.py:253
 REFRESH_BATCH_SIZE = 50  # README.md:42 (code default 100, app/config.py:255); BASELINE.json uses 50
 
-__all__ = ["Index", "Filter", "PgCopyLoader", "encode_copy_binary", "parse_vector_text", "QueryBatcher", "IndexServer", "RemoteIndex", "serve_in_thread", "GpuVectorStore", "GpuRetriever", "MemoryDocStore", "Document", "OrxError",
+__all__ = ["Index", "Filter", "PgCopyLoader", "encode_copy_binary", "SqlDocStore", "vector_to_text", "parse_vector_text", "QueryBatcher", "IndexServer", "RemoteIndex", "serve_in_thread", "GpuVectorStore", "GpuRetriever", "MemoryDocStore", "Document", "OrxError",
            "OrxValueError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device",
            "build", "version", "ORX_DIM", "ORX_MAX_K", "DTYPE_F32", "DTYPE_BF16", "TOP_K",
            "REFRESH_BATCH_SIZE"]
