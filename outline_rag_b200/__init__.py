@@ -9,6 +9,7 @@ from ._lib import (DTYPE_BF16, DTYPE_F32, ORX_DIM, ORX_MAX_K, OrxError, OrxValue
 from .batcher import QueryBatcher
 from .daemon import IndexServer, RemoteIndex, serve_in_thread
 from .engine import Filter, Index, PgCopyLoader, parse_vector_text, ids_to_array, ids_to_ints, ids_to_uuid_strs, synth_rows_device
+from . import pgwire
 from .docstore_sql import SqlDocStore, vector_to_text
 from .pgwire import encode_copy_binary
 from .vectorstore import Document, GpuRetriever, GpuVectorStore, MemoryDocStore

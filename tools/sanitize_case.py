@@ -1,7 +1,8 @@
 """Small end-to-end case for compute-sanitizer (memcheck / racecheck / synccheck):
     gpurun -- compute-sanitizer --tool memcheck python tools/sanitize_case.py
 Covers upsert, delete (compaction), GEMV scan, tcgen05 scan (both dtypes), the exhaustive fallback,
-the single-rank sharded exchange, snapshot export/import; checks results against the oracle."""
+the single-rank sharded exchange, snapshot export/import, the COPY BINARY decode (odd payload alignment) and
+the bitmap-filtered scan; checks results against the oracle."""
 import os
 import sys
 import tempfile
@@ -43,4 +44,21 @@ for dtype in ("fp32", "bf16"):
             jx = orx.Index.load(d)
             assert np.array_equal(jx.search(Q[:3], 12)[0], p[0][:3])
             jx.close()
+        # cold-start decode: a 3-byte header extension shifts the payloads to byte alignments 0 and 2 (tests use 1 and 3)
+        stream = orx.pgwire.COPY_HEADER[:15] + (3).to_bytes(4, "big") + b"xyz" + orx.pgwire.encode_tuples(ids[:300], X[:300]) \
+            + orx.pgwire.COPY_TRAILER
+        with orx.Index(dtype) as kx:
+            assert kx.load_pgcopy([stream[:100_001], stream[100_001:]]) == (300, 0)
+            got, found = kx.fetch(ids[:300])
+            assert found.all() and np.array_equal(got, rows[:300])
+        # bitmap-filtered scan over 4500 of the live rows (+ the handle form)
+        live = np.nonzero(keep)[0]
+        sel = live[:4500]
+        f = ix.search_filtered(Q[:3], 12, ids[sel])
+        with ix.make_filter(ids[sel]) as flt:
+            h = ix.search_filtered(Q[:3], 12, flt)
+        for i in range(3):
+            w_ids, w_d = O.topk_exact(rows[sel], ids[sel], Q[i], 12)
+            assert np.array_equal(f[0][i], w_ids) and np.array_equal(h[0][i], w_ids)
+            assert np.array_equal(f[1][i].view(np.uint64), w_d.view(np.uint64))
 print("sanitize case ok")
