@@ -26,6 +26,7 @@ from typing import Any, Iterable, Optional, Sequence
 
 import numpy as np
 
+from ._lib import ORX_DIM, ORX_ERR_DIM, ORX_ERR_NONFINITE, OrxValueError
 from .batcher import QueryBatcher
 from .engine import Filter, Index, ids_to_array, ids_to_uuid_strs
 
@@ -194,14 +195,27 @@ class GpuVectorStore:
             ids = [None] * n
         ids = [_canon_uuid(i) if i is not None else str(uuid.uuid4()) for i in ids]   # `doc.id or uuid4()`
         metadatas = list(metadatas) if metadatas is not None else [{} for _ in range(n)]
-        emb = np.asarray(embeddings, dtype=np.float32)
         if n == 0:
             return []
-        self.index.upsert(ids, emb)                      # raises on wrong dim / NaN, nothing stored
+        try:
+            emb = np.asarray(embeddings, dtype=np.float32)
+        except ValueError:                                # ragged: some vector has another length
+            lens = sorted({len(e) for e in embeddings} - {ORX_DIM})
+            raise OrxValueError(ORX_ERR_DIM, f"expected {ORX_DIM} dimensions, not {lens[0] if lens else '?'}") from None
+        # pgvector's input checks, before anything is written anywhere (the reference's INSERT fails as a
+        # whole for such a batch, rag.py:237-239 re-raises): same conditions and messages as orx_upsert
+        if emb.ndim != 2 or emb.shape[0] != n or emb.shape[1] != ORX_DIM:
+            got = emb.shape[-1] if emb.ndim >= 1 and emb.size else 0
+            raise OrxValueError(ORX_ERR_DIM, f"expected {ORX_DIM} dimensions, not {got}")
+        if not np.isfinite(emb).all():
+            raise OrxValueError(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector")
+        # durable copy first (Postgres stays the source of truth; if this raises, the device table is untouched),
+        # then the device table, which is a cache of it: a failure there is healed by a reload
         if getattr(self.doc_store, "stores_embeddings", False):
-            self.doc_store.put_many(ids, list(texts), metadatas, embeddings=emb)     # durable copy (cold start)
+            self.doc_store.put_many(ids, list(texts), metadatas, embeddings=emb)
         else:
             self.doc_store.put_many(ids, list(texts), metadatas)
+        self.index.upsert(ids, emb)
         return ids
 
     async def aadd_embeddings(self, texts, embeddings, metadatas=None, ids=None) -> list[str]:

@@ -238,3 +238,37 @@ def test_prepared_filter_skips_the_doc_store_lookup(small_table):
     assert lookups == []                                    # the prepared handle bypassed the doc store
     store.similarity_search_with_score_by_vector(X[12], 5, filter={"source_id": "d1"})
     assert lookups == [{"source_id": "d1"}]
+
+
+def test_a_failed_batch_leaves_doc_store_and_index_untouched(small_table):
+    """`aadd_documents` is all-or-nothing like the reference's INSERT: invalid vectors are rejected before any
+    write, and when the durable write fails the device table is not touched either."""
+    import outline_rag_b200 as orx
+    X, _, _ = small_table
+
+    class Emb(FakeEmb):
+        async def aembed_documents(self, texts):
+            return [self.bad if t == "bad" else self.X[int(t)] for t in texts]
+
+    class FlakyStore(orx.MemoryDocStore):
+        fail = False
+
+        def put_many(self, *a, **kw):
+            if self.fail:
+                raise ConnectionError("server closed the connection unexpectedly")
+            return super().put_many(*a, **kw)
+
+    owner = FakeStoreIndex(np.zeros((0, 1024), np.float32), np.zeros((0, 2), np.uint64))
+    emb, docs_store = Emb(X), FlakyStore()
+    store = orx.GpuVectorStore(owner, emb, doc_store=docs_store)
+    good = [orx.Document(page_content=str(i), id=str(uuid.UUID(int=i + 1))) for i in range(5)]
+    asyncio.run(store.aadd_documents(good))
+    for bad, msg in ((np.full(1024, np.nan, np.float32), "NaN or infinite"), (np.zeros(768, np.float32), "expected 1024 dimensions")):
+        emb.bad = bad
+        with pytest.raises(orx.OrxValueError, match=msg):
+            asyncio.run(store.aadd_documents([orx.Document(page_content="7"), orx.Document(page_content="bad")]))
+        assert len(owner) == 5 and len(docs_store._rows) == 5
+    docs_store.fail = True
+    with pytest.raises(ConnectionError):
+        asyncio.run(store.aadd_documents([orx.Document(page_content="8")]))
+    assert len(owner) == 5 and [op for op, _ in owner.log] == ["upsert"]
