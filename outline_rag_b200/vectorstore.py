@@ -247,8 +247,8 @@ class GpuVectorStore:
         if not ids:
             return False
         sids = [_canon_uuid(i) for i in ids]
+        self.doc_store.delete_many(sids)                 # source of truth first; if it raises nothing changed
         self.index.delete(sids)
-        self.doc_store.delete_many(sids)
         return True
 
     async def adelete(self, ids: Optional[Sequence] = None, **kw: Any) -> bool:
