@@ -201,12 +201,6 @@ int orx_pgcopy_close(orx_pgcopy *ld, uint64_t *rows_loaded, uint64_t *rows_null)
  * dimension -> ORX_ERR_DIM, NaN / infinity -> ORX_ERR_NONFINITE. */
 int orx_parse_vector_text(const char *text, uint64_t len, float *out, int dim);
 
-/* Synthetic bge-m3-shaped table generator, bit-identical to
- * outline_rag_b200/synth.py.  Fills dst_device [n_rows, 1024] fp32 with rows
- * row_start .. row_start+n_rows-1.  centres/mean are built on first use. */
-int orx_synth_rows(int device, void *cuda_stream, uint64_t seed, uint32_t n_centres,
-                   uint64_t row_start, uint64_t n_rows, float *dst_device);
-
 const char *orx_last_error(void);
 const char *orx_version(void);
 

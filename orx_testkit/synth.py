@@ -10,7 +10,7 @@ the remote bge-m3 embedding service of the reference
 The recipe is COUNTER-BASED and uses only exactly-rounded IEEE operations in a
 fixed order (integer hash -> Irwin-Hall(4) of 16-bit fields -> fp32 mul/add ->
 binary64 halving-tree norm -> fp32 scale), so that the CUDA generator in
-``csrc/synth.cu`` (``orx_synth_*``) produces the SAME BITS for any row index.
+``orx_testkit/csrc/synth.cu`` (``orxtk_synth_rows``) produces the SAME BITS for any row index.
 That lets a 10M-row table be generated on the device while the host regenerates
 any individual row for sampled verification, and lets the CPU reference arm of
 ``bench.py`` run on identical data.  tests/test_synth.py checks host == device.

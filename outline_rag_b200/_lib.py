@@ -10,9 +10,14 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("ORX_LIB") or os.path.join(_HERE, "liborx.so")   # ORX_LIB: A/B builds side by side
+# The library is the in-tree build, full stop: no environment variable can swap it.  Same-box A/B measurements of an
+# experimental build (`make -C csrc variant NAME=x`) select it IN PROCESS, before the first import of this package,
+# by registering a module object: sys.modules["orx_lib_override"] = SimpleNamespace(LIB_PATH=...)  (bench.py --lib).
+_override = getattr(sys.modules.get("orx_lib_override"), "LIB_PATH", None)
+LIB_PATH = _override or os.path.join(_HERE, "liborx.so")
 CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ORX_DIM = 1024
@@ -95,7 +100,6 @@ SIGNATURES = {
     "orx_pgcopy_feed": (C.c_int, [_vp, _vp, C.c_uint64]),
     "orx_pgcopy_close": (C.c_int, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "orx_parse_vector_text": (C.c_int, [C.c_char_p, C.c_uint64, _vp, C.c_int]),
-    "orx_synth_rows": (C.c_int, [C.c_int, _vp, C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint64, _vp]),
     "orx_last_error": (C.c_char_p, []),
     "orx_version": (C.c_char_p, []),
 }

@@ -438,7 +438,7 @@ void launch_collect(int dtype, const void *table, const float *scale, uint32_t n
                     const float *qhat, float fast_floor, int collect_all, uint32_t *list,
                     uint32_t *count, cudaStream_t st) {
     if (n_rows == 0) return;
-    const int grid = 148 * 4;
+    const int grid = device_sms() * 4;
     if (dtype == ORX_DTYPE_F32)
         collect_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(table), scale, n_rows,
                                                     qhat, fast_floor, collect_all, list, count);
@@ -469,7 +469,7 @@ rescore_list_kernel(const T *__restrict__ table, const double *__restrict__ n2,
 void launch_rescore_list(int dtype, const void *table, const double *n2, const orx_id *,
                          const float *q, const QueryPrep *prep, const uint32_t *list,
                          const uint32_t *count, double *dist_out, cudaStream_t st) {
-    const int grid = 148 * 2;
+    const int grid = device_sms() * 2;
     if (dtype == ORX_DTYPE_F32)
         rescore_list_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float *>(table), n2, q,
                                                          prep, list, count, dist_out);

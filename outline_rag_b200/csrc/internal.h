@@ -84,17 +84,17 @@ void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint
 void launch_decode_pgvector(const uint8_t *raw, const uint64_t *payload_off, uint32_t n, float *out,
                             cudaStream_t st);
 
+// SM count of the CURRENT device (cached per device): launch geometry is sized from it, never from a literal
+int device_sms();
+template <typename T> inline T cap_grid(T blocks, int ctas_per_sm) {     // persistent-style grids: <= ctas_per_sm x SMs
+    const T cap = (T)device_sms() * (T)ctas_per_sm;
+    return blocks > cap ? cap : blocks;
+}
+
 // ---- orx_api.cu: what the other translation units need from an index
 int set_error(int code, const char *fmt, ...);     // records the thread-local message, returns code
 cudaStream_t index_stream(const orx_index *ix);
 int index_device(const orx_index *ix);
 void index_count_launches(orx_index *ix, uint64_t n);
-
-// ---- synth.cu
-void launch_synth_unit(uint64_t key, uint32_t n_vec, float *dst, cudaStream_t st);
-void launch_synth_rows(uint64_t key_noise, uint64_t key_cid, const float *mean, const float *centres,
-                       uint32_t n_centres, uint64_t row_start, uint64_t n_rows, float *dst,
-                       cudaStream_t st);
-uint64_t synth_stream_key(uint64_t seed, uint64_t tag);
 
 }  // namespace orx

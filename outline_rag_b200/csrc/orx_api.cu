@@ -10,7 +10,6 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <map>
 #include <mutex>
 #include <string>
 #include <unordered_map>
@@ -147,7 +146,7 @@ struct orx_index {
     uint64_t capacity = 0;
     uint64_t n_live = 0;
     uint64_t generation = 0;            // bumped whenever the id -> row map changes (orx_filter re-resolves then)
-    int scan_grid_sms = 148;
+    int scan_grid_sms = 0;              // multiProcessorCount of `device` (orx_create)
 
     // the table (device)
     void *table = nullptr;
@@ -772,6 +771,17 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
 }  // namespace
 
 namespace orx {
+int device_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 1;
+    int v = cache[dev];
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 1;
+        cache[dev] = v;
+    }
+    return v;
+}
 int set_error(int code, const char *fmt, ...) {
     char buf[512];
     va_list ap;
@@ -1376,45 +1386,6 @@ int orx_fetch(orx_index *ix, const orx_id *ids, uint64_t n, float *out_vecs, int
         CK(cudaMemcpyAsync(out_vecs + s * ORX_DIM, ix->stage.p, m * ORX_DIM * sizeof(float), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
-    CK(cudaGetLastError());
-    return ORX_OK;
-}
-
-namespace {
-struct SynthState {
-    float *mean = nullptr, *centres = nullptr;
-};
-std::mutex g_synth_mu;
-std::map<std::tuple<int, uint64_t, uint32_t>, SynthState> g_synth;
-}  // namespace
-
-int orx_synth_rows(int device, void *cuda_stream, uint64_t seed, uint32_t n_centres, uint64_t row_start,
-                   uint64_t n_rows, float *dst_device) {
-    if (n_centres == 0) return fail(ORX_ERR_INVALID, "n_centres must be > 0");
-    if (n_rows == 0) return ORX_OK;
-    if (!is_device_ptr(dst_device)) return fail(ORX_ERR_INVALID, "dst must be a device pointer");
-    DeviceGuard g(device);
-    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    // stream tags: outline_rag_b200/synth.py TAG_*
-    const uint64_t k_mean = orx::synth_stream_key(seed, 0x6D65616Eull);
-    const uint64_t k_centre = orx::synth_stream_key(seed, 0x63656E74ull);
-    const uint64_t k_noise = orx::synth_stream_key(seed, 0x6E6F6973ull);
-    const uint64_t k_cid = orx::synth_stream_key(seed, 0x63696421ull);
-    SynthState ss;
-    {
-        std::lock_guard<std::mutex> lk(g_synth_mu);
-        auto key = std::make_tuple(device, seed, n_centres);
-        auto it = g_synth.find(key);
-        if (it == g_synth.end()) {
-            CK(cudaMalloc(&ss.mean, ORX_DIM * sizeof(float)));
-            CK(cudaMalloc(&ss.centres, (size_t)n_centres * ORX_DIM * sizeof(float)));
-            orx::launch_synth_unit(k_mean, 1, ss.mean, st);
-            orx::launch_synth_unit(k_centre, n_centres, ss.centres, st);
-            CK(cudaStreamSynchronize(st));
-            g_synth.emplace(key, ss);
-        } else ss = it->second;
-    }
-    orx::launch_synth_rows(k_noise, k_cid, ss.mean, ss.centres, n_centres, row_start, n_rows, dst_device, st);
     CK(cudaGetLastError());
     return ORX_OK;
 }

@@ -56,7 +56,7 @@ decode_pgvector_kernel(const uint8_t *__restrict__ raw, const uint64_t *__restri
 void launch_decode_pgvector(const uint8_t *raw, const uint64_t *off, uint32_t n, float *out, cudaStream_t st) {
     if (n == 0) return;
     uint32_t blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks = cap_grid(blocks, 8);
     decode_pgvector_kernel<<<blocks, 256, 0, st>>>(raw, off, n, out);
 }
 

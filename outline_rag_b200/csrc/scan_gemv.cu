@@ -183,8 +183,8 @@ scan_gemv_filtered_kernel(const T *__restrict__ table, const float *__restrict__
 }
 
 int scan_gemv_grid(int device, uint32_t n_rows) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 1;
     constexpr int ROWS_PER_ITER = 2;      // grid sizing only: enough chunks for every warp of the persistent grid
     uint32_t chunks = (n_rows + ROWS_PER_ITER - 1) / ROWS_PER_ITER;
     uint32_t want = (chunks + SCAN_WARPS - 1) / SCAN_WARPS;

@@ -134,6 +134,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the staged 1/|x| values go through explicit shared-space instructions (a generic pointer derived from the
+// aligned dynamic-smem base compiles to LD.E / ST.E, which take the slower generic path)
+__device__ __forceinline__ float4 lds_f4(uint32_t addr) {
+    float4 r;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float r;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(addr) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+// Timing experiments (skip the column scan / the query loads / the table loads: results are garbage) exist ONLY in
+// builds made with -DORX_DEBUG_VARIANTS (`make variant NAME=dbg DEFS=-DORX_DEBUG_VARIANTS`); the product library
+// contains neither the code paths nor the ORX_UMMA_DEBUG / ORX_UMMA_PAIRS environment look-ups.
+#ifdef ORX_DEBUG_VARIANTS
+#define ORX_DBG_PARAM , int dbg
+#define ORX_DBG_ARG(p) , (p)->dbg
+#define ORX_DBG_FWD , dbg
+#define ORX_DBG(bit) (dbg & (bit))
+#else
+#define ORX_DBG_PARAM
+#define ORX_DBG_ARG(p)
+#define ORX_DBG_FWD
+#define ORX_DBG(bit) 0
+#endif
 
 // ---- CTA-pair (cta_group::2) variants
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -245,8 +275,8 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
                                               const float *__restrict__ scale, uint32_t n_rows, int k, float margin,
                                               uint64_t *__restrict__ partial, float *__restrict__ floor_out,
                                               uint32_t *__restrict__ gthr_all, float *s_scale, uint32_t bar_tfull,
-                                              uint32_t tmem_base, int ew, int lane, ArriveEmpty arrive_empty,
-                                              int dbg = 0) {
+                                              uint32_t tmem_base, int ew, int lane, ArriveEmpty arrive_empty
+                                              ORX_DBG_PARAM) {
     const int et = ew * 32 + lane;                          // 0..127
     const int q = q_base + ew * 32 + lane;
     const bool active = q < nq;
@@ -266,13 +296,13 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
     for (uint32_t t = slot; t < n_tiles; t += n_slots) {
         const uint32_t n0 = t * TILE_N;
         // stage this tile's 1/|x| (NaN beyond the table end: never a candidate)
-        float *sc = s_scale + buf * TILE_N;
+        const uint32_t sc = smem_u32(s_scale) + buf * TILE_N * 4;
         bool special = false;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float s = sc_next[h];
             special |= !(fabsf(s) < __int_as_float(0x7f800000));      // inf or NaN
-            sc[et + 128 * h] = s;
+            sts_f32(sc + 4 * (et + 128 * h), s);
             const uint32_t rn = n0 + (uint32_t)n_slots * TILE_N + et + 128 * h;
             sc_next[h] = (t + n_slots < n_tiles && rn < n_rows) ? __ldg(scale + rn) : __int_as_float(0x7fc00000);
         }
@@ -289,16 +319,15 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + buf * TILE_N;
 #pragma unroll 1
-        for (int c = 0; c < ((dbg & 1) ? 0 : TILE_N / 32); ++c) {      // dbg bit 0: timing experiment, no column scan
+        for (int c = 0; c < (ORX_DBG(1) ? 0 : TILE_N / 32); ++c) {
             uint32_t v[32];
             tmem_ld32(taddr + c * 32, v);
             tmem_ld_wait();
-            const float4 *sc4 = reinterpret_cast<const float4 *>(sc + c * 32);
             float s[32];
             float mx = __int_as_float(0xff800000);
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 f = sc4[j4];
+                const float4 f = lds_f4(sc + 4 * (c * 32 + 4 * j4));
                 s[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * f.x;
                 s[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * f.y;
                 s[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * f.z;
@@ -313,7 +342,7 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
             if (tile_special) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float sj = sc[c * 32 + j];
+                    const float sj = lds_f32(sc + 4 * (c * 32 + j));
                     if (sj == __int_as_float(0x7f800000)) always |= 1u << j;      // irregular magnitude
                     else if (sj != sj) s[j] = __int_as_float(0xff800000);         // zero-norm / beyond the end
                 }
@@ -369,7 +398,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const float *__restrict__ scale, uint32_t n_rows, int nq, int m_tiles, int n_slots, int k,
                  float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
-                 uint32_t *__restrict__ gthr_all, int dbg) {
+                 uint32_t *__restrict__ gthr_all ORX_DBG_PARAM) {
     constexpr int ES = TF32 ? 4 : 2;                // operand element size
     constexpr int BLOCK_K = 128 / ES;               // elements per 128-byte swizzle row
     constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;     // 16 (bf16) / 32 (tf32)
@@ -424,11 +453,10 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
                 for (int kc = 0; kc < K_CHUNKS; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     const uint32_t sa = smem_base + stage * STAGE_BYTES;
-                    // dbg bits 1 / 2 (timing experiments only): do not load the query / table operand
-                    mbar_expect_tx(bar_full + 8 * stage, ((dbg & 2) ? 0 : A_BYTES) + ((dbg & 4) ? 0 : B_BYTES));
-                    if (!(dbg & 2))
+                    mbar_expect_tx(bar_full + 8 * stage, (ORX_DBG(2) ? 0 : A_BYTES) + (ORX_DBG(4) ? 0 : B_BYTES));
+                    if (!ORX_DBG(2))
                         tma_load_2d(sa, &map_q, bar_full + 8 * stage, kc * BLOCK_K, m_tile * TILE_M, HINT_EVICT_LAST);
-                    if (!(dbg & 4))
+                    if (!ORX_DBG(4))
                         tma_load_2d(sa + A_BYTES, &map_x, bar_full + 8 * stage, kc * BLOCK_K, (int)(t * TILE_N), hint_x);
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -462,7 +490,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         // ========================================================================= epilogue
         epilogue_loop(m_tile * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin, partial, floor_out,
                       gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
-                      [&](uint32_t b) { mbar_arrive(bar_tempty + 8 * b); }, dbg);
+                      [&](uint32_t b) { mbar_arrive(bar_tempty + 8 * b); } ORX_DBG_FWD);
     }
 
     tc_fence_before();
@@ -486,7 +514,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                   const float *__restrict__ scale, uint32_t n_rows, int nq, int m_pairs, int n_slots, int k,
                   float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
-                  uint32_t *__restrict__ gthr_all, int dbg) {
+                  uint32_t *__restrict__ gthr_all ORX_DBG_PARAM) {
     constexpr int ES = TF32 ? 4 : 2;
     constexpr int BLOCK_K = 128 / ES;
     constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;
@@ -546,11 +574,11 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
                     const uint32_t sa = smem_base + stage * STAGE2_BYTES;
                     const uint32_t full_leader = map_to_cta(bar_full + 8 * stage, 0);
                     if (leader)
-                        mbar_expect_tx(bar_full + 8 * stage, 2 * (((dbg & 2) ? 0 : A_BYTES) + ((dbg & 4) ? 0 : B2_BYTES)));
-                    if (!(dbg & 2))
+                        mbar_expect_tx(bar_full + 8 * stage, 2 * ((ORX_DBG(2) ? 0 : A_BYTES) + (ORX_DBG(4) ? 0 : B2_BYTES)));
+                    if (!ORX_DBG(2))
                         tma_load_2d_pair(sa, &map_q, full_leader, kc * BLOCK_K,
                                          m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, HINT_EVICT_LAST);
-                    if (!(dbg & 4))
+                    if (!ORX_DBG(4))
                         tma_load_2d_pair(sa + A_BYTES, &map_x, full_leader, kc * BLOCK_K,
                                          (int)(t * TILE_N) + (int)cta_rank * (TILE_N / 2), hint_x);
                     if (++stage == STAGES2) { stage = 0; phase ^= 1; }
@@ -586,7 +614,7 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
         const uint32_t tempty_leader = map_to_cta(bar_tempty, 0);
         epilogue_loop(m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
                       partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
-                      [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); }, dbg);
+                      [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); } ORX_DBG_FWD);
     }
 
     tc_fence_before();
@@ -641,10 +669,12 @@ bool encode_map(CUtensorMap *map, const void *base, uint64_t rows, bool fp32, ui
 
 struct UmmaPlan {
     int device = 0;
-    int sms = 148;
+    int sms = 1;
     bool attr_set = false;
+#ifdef ORX_DEBUG_VARIANTS
     int dbg = 0;                     // ORX_UMMA_DEBUG: timing experiments (results are garbage when set)
-    bool use_pairs = true;           // ORX_UMMA_PAIRS=0 keeps every batch on the 1-CTA kernel (A/B measurements)
+#endif
+    bool use_pairs = true;           // variant builds: ORX_UMMA_PAIRS=0 keeps every batch on the 1-CTA kernel
     uint64_t *partial = nullptr;
     size_t partial_n = 0;
     float *floor = nullptr;
@@ -658,10 +688,12 @@ UmmaPlan *umma_plan_create(int device) {
     UmmaPlan *p = new UmmaPlan();
     p->device = device;
     cudaDeviceGetAttribute(&p->sms, cudaDevAttrMultiProcessorCount, device);
+#ifdef ORX_DEBUG_VARIANTS
     const char *env = getenv("ORX_UMMA_PAIRS");
     if (env && env[0] == '0') p->use_pairs = false;
     env = getenv("ORX_UMMA_DEBUG");
     if (env) p->dbg = atoi(env);
+#endif
     return p;
 }
 void umma_plan_destroy(UmmaPlan *p) {
@@ -734,24 +766,26 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
             const int grid = 2 * m_tiles * n_slots;
             if (tf32)
                 scan_umma2_kernel<true><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                               k, margin, p->partial, p->floor, p->gthr, p->dbg);
+                                                                               k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
             else
                 scan_umma2_kernel<false><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                                k, margin, p->partial, p->floor, p->gthr, p->dbg);
+                                                                                k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
         } else {
             const int grid = m_tiles * n_slots;
             if (tf32)
                 scan_umma_kernel<true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                             k, margin, p->partial, p->floor, p->gthr, p->dbg);
+                                                                             k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
             else
                 scan_umma_kernel<false><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                              k, margin, p->partial, p->floor, p->gthr, p->dbg);
+                                                                              k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
         }
         if (ev_end && q0 + MAX_Q >= nq) cudaEventRecord(ev_end, st);
         launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, 2, m,
                         k, n_rows, eps, out_ids + (size_t)q0 * k, out_dist + (size_t)q0 * k, out_counts + q0,
                         out_flags + q0, st, p->floor);
+#ifdef ORX_DEBUG_VARIANTS
         if (p->dbg) launch_flags_from_prep(prep + q0, m, out_flags + q0, st);   // timing experiments: no fallbacks
+#endif
         *launch_counter += 2;
         e = cudaGetLastError();
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }

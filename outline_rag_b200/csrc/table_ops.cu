@@ -28,7 +28,7 @@ void launch_validate_rows(const float *src, uint64_t n, int *flag, cudaStream_t 
     if (n == 0) return;
     const uint64_t n4 = n * (ORX_DIM / 4);
     uint64_t blocks = (n4 + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    blocks = cap_grid(blocks, 16);
     validate_rows_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4 *>(src), n4, flag);
 }
 
@@ -89,7 +89,7 @@ void launch_commit_rows(int dtype, const float *src, const uint32_t *src_idx, co
                         orx_id *row_ids, cudaStream_t st) {
     if (n == 0) return;
     uint32_t blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks = cap_grid(blocks, 8);
     if (dtype == ORX_DTYPE_F32)
         commit_rows_kernel<float><<<blocks, 256, 0, st>>>(src, src_idx, dst_row, ids, n,
                                                           static_cast<float *>(table), scale, n2, row_ids);
@@ -135,7 +135,7 @@ void launch_adopt_rows(int dtype, const void *table, uint32_t row0, uint32_t n, 
                        double *n2, orx_id *row_ids, int *flag, cudaStream_t st) {
     if (n == 0) return;
     uint32_t blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks = cap_grid(blocks, 8);
     if (dtype == ORX_DTYPE_F32)
         adopt_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(table), row0, n, ids, scale, n2,
                                                          row_ids, flag);
@@ -170,7 +170,7 @@ void launch_move_rows(int dtype, const uint32_t *src_row, const uint32_t *dst_ro
                       void *table, float *scale, double *n2, orx_id *row_ids, cudaStream_t st) {
     if (n == 0) return;
     uint32_t blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks = cap_grid(blocks, 8);
     const int vpr = dtype == ORX_DTYPE_F32 ? 256 : 128;
     move_rows_kernel<<<blocks, 256, 0, st>>>(src_row, dst_row, n, static_cast<uint4 *>(table), vpr,
                                              scale, n2, row_ids);
@@ -198,7 +198,7 @@ void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint
                         cudaStream_t st) {
     if (n == 0) return;
     uint32_t blocks = (n + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    blocks = cap_grid(blocks, 8);
     if (dtype == ORX_DTYPE_F32)
         gather_rows_kernel<float><<<blocks, 256, 0, st>>>(static_cast<const float *>(table), rows, n, out);
     else

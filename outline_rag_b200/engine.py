@@ -352,6 +352,15 @@ class Index:
     # -- snapshot / cold start
     SNAPSHOT_CHUNK = 65536
 
+    def export_rows(self, row_start: int, n: int, ids_out: np.ndarray, rows_out: np.ndarray) -> None:
+        """Live rows [row_start, row_start+n) VERBATIM in the table dtype + their ids into caller-owned host
+        buffers (`orx_export_rows`; pinned buffers make it a PCIe-rate copy).  Row order is table order."""
+        rb = ORX_DIM * (4 if self.dtype == "fp32" else 2)
+        if ids_out.nbytes < n * 16 or rows_out.nbytes < n * rb or not ids_out.flags.c_contiguous or not rows_out.flags.c_contiguous:
+            raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "export buffers too small or not contiguous")
+        check(lib.orx_export_rows(self._h, int(row_start), int(n), C.c_void_p(ids_out.ctypes.data),
+                                  C.c_void_p(rows_out.ctypes.data)))
+
     def save(self, path: str) -> dict:
         """Write `manifest.json`, `ids.bin` (uint64 [n,2]) and `vecs.bin` (rows verbatim in the table
         dtype) under `path`.  Postgres stays the source of truth; this avoids re-loading 41 GB of
@@ -458,15 +467,4 @@ class Index:
         return oi, od, oc
 
 
-def synth_rows_device(device: int, seed: int, n_centres: int, row_start: int, n_rows: int, out=None):
-    """Rows ``row_start .. row_start+n_rows-1`` of the synthetic table, generated in HBM
-    (bit-identical to ``synth.Synth.rows``).  Returns a float32 CUDA tensor."""
-    if out is None:
-        out = torch.empty((n_rows, ORX_DIM), dtype=torch.float32, device=f"cuda:{device}")
-    stream = torch.cuda.current_stream(device).cuda_stream
-    check(lib.orx_synth_rows(int(device), C.c_void_p(stream), int(seed), int(n_centres), int(row_start),
-                             int(n_rows), C.c_void_p(out.data_ptr())))
-    return out
-
-
-__all__ = ["Index", "Filter", "PgCopyLoader", "parse_vector_text", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs", "synth_rows_device"]
+__all__ = ["Index", "Filter", "PgCopyLoader", "parse_vector_text", "OrxError", "ids_to_array", "ids_to_ints", "ids_to_uuid_strs"]

@@ -52,7 +52,7 @@ def pgv_lib():
 @pytest.fixture(scope="session")
 def synth100k():
     """Generator state for the 100k-row config (1024 centres), SURVEY.md 8(d)."""
-    from outline_rag_b200.synth import Synth
+    from orx_testkit.synth import Synth
     return Synth(1024)
 
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import cosine_topk as O            # noqa: E402
-from outline_rag_b200.synth import Synth       # noqa: E402
+from orx_testkit.synth import Synth       # noqa: E402
 from tests._helpers import stored_bf16_rows          # noqa: E402
 
 N_ROWS, N_QUERIES, K = 20000, 16, 12

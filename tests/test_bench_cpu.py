@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_the_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--rows", "50000",
-                          "--cpu-sample-rows", "20000", "--steps", "2", "--warmup", "1"],
+                          "--steps", "3", "--warmup", "1"],
                          capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
@@ -18,9 +18,24 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["gpu_launches"] == 0
     assert "50000x1024" in line["config"]["workload"]
-    pgv = line["cpu_baseline"]["pgvector_loop"]                  # the C restatement of pgvector's scan loop, timed too
-    assert pgv["one_backend"]["threads"] == 1 and pgv["one_backend"]["queries_per_s"] > 0
-    assert pgv["parallel_seq_scan"]["queries_per_s"] > 0
+    cb = line["cpu_baseline"]
+    pgv = cb["pgvector_loop"]                                    # the C restatement of pgvector's scan loop, timed too
+    assert pgv["one_backend"]["threads"] == 1 and pgv["one_backend"]["p50_ms_measured"] > 0
+    assert pgv["parallel_seq_scan"]["queries_per_s_at_full_rows_extrapolated"] > 0
+    # BASELINE.json configs[0] (100k rows) is measured as stated; 50k rows <= 1M are measured, not extrapolated
+    assert cb["measured"][0]["rows"] == 100_000 and cb["measured"][0]["extrapolated"] is False
+    assert cb["measured"][1]["rows"] == 50_000 and cb["extrapolated"] is False
+    assert line["config"]["rows"] == 50_000 and line["config"]["batch"] == 1
+
+
+def test_reference_arm_loads_no_product_library():
+    """The CPU arm's process must not map liborx.so (it did, through the package __init__)."""
+    code = ("import sys, types; sys.argv=['bench.py','--impl','reference','--rows','20000','--steps','2','--warmup','1'];"
+            "import runpy; runpy.run_path('bench.py', run_name='__main__');"
+            "maps=open('/proc/self/maps').read(); assert 'liborx' not in maps, 'product library mapped';"
+            "assert 'outline_rag_b200' not in sys.modules; print('CLEAN')")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0 and "CLEAN" in out.stdout, out.stderr[-2000:]
 
 
 def test_non_zero_ranks_of_the_reference_arm_exit_quietly():

@@ -93,7 +93,7 @@ CHILD = r"""
 import json, sys, numpy as np
 sys.path.insert(0, sys.argv[1])
 from outline_rag_b200.daemon import RemoteIndex
-from outline_rag_b200.synth import Synth
+from orx_testkit.synth import Synth
 syn = Synth(1024)
 Q, _ = syn.queries(4, 8192)
 ix = RemoteIndex(sys.argv[2])

@@ -219,3 +219,56 @@ def test_canonical_distance_is_within_an_ulp_of_exact_arithmetic(seed):
     exact = 1.0 - math.fsum(xd * qd) / math.sqrt(math.fsum(xd * xd) * math.fsum(qd * qd))
     assert abs(d - exact) <= 1e-14
     assert O.canon_distance(x[None, :] * np.float32(4.0), q * np.float32(0.5))[0] == d      # scale-free, exactly
+
+
+# ---------------------------------------------------------------- streaming full scan (bench.py verify, 1M-row tests)
+def test_streaming_full_scan_equals_topk_exact(small_table):
+    """`StreamingTopK` (fp32 BLAS shortlist per chunk, canonical rescoring of the shortlist) is what checks the
+    engine at sizes `topk_exact` cannot take; it must give the same ids and distance bits, also with zero-norm,
+    tiny-norm and duplicated rows in the table and when rows arrive as raw bf16."""
+    from tests._helpers import bf16_rne
+    X, Q, _ = small_table
+    X = X.copy()
+    X[100] = 0.0
+    X[200] *= np.float32(1e-25)
+    X[300] = X[7]
+    ids = _ids(X.shape[0], start=2**40)
+    st = O.StreamingTopK(Q[:6], K)
+    for s in range(0, X.shape[0], 3000):
+        st.feed(X[s:s + 3000], ids[s:s + 3000])
+    assert st.rows_seen == X.shape[0]
+    for j, (g_ids, g_d) in enumerate(st.result()):
+        w_ids, w_d = O.topk_exact(X, ids, Q[j], K)
+        assert np.array_equal(g_ids, w_ids) and np.array_equal(g_d.view(np.uint64), w_d.view(np.uint64)), j
+    # bf16 rows fed as raw bit patterns
+    Xb = bf16_rne(X)
+    raw = (Xb.view(np.uint32) >> np.uint32(16)).astype(np.uint16)
+    st = O.StreamingTopK(Q[:3], K)
+    st.feed(raw, ids, rows_are_bf16=True)
+    for j, (g_ids, g_d) in enumerate(st.result()):
+        w_ids, w_d = O.topk_exact(Xb, ids, Q[j], K)
+        assert np.array_equal(g_ids, w_ids) and np.array_equal(g_d.view(np.uint64), w_d.view(np.uint64)), j
+    # fewer finite rows than k: NaN rows complete the answer in id order
+    Xs = X[:8].copy()
+    Xs[3] = 0.0
+    st = O.StreamingTopK(Q[:1], K)
+    st.feed(Xs, ids[:8])
+    (g_ids, g_d), = st.result()
+    w_ids, w_d = O.topk_exact(Xs, ids[:8], Q[0], K)
+    assert np.array_equal(g_ids, w_ids) and np.array_equal(g_d.view(np.uint64), w_d.view(np.uint64))
+
+
+def test_streaming_candidates_merge_across_shards(small_table):
+    """What bench.py does at N > 1: per-shard `candidates()` merged by `merge_shards` == the global answer."""
+    X, Q, _ = small_table
+    ids = _ids(X.shape[0])
+    parts = np.arange(X.shape[0]) % 3
+    shards = []
+    for p in range(3):
+        st = O.StreamingTopK(Q[:4], K)
+        st.feed(X[parts == p], ids[parts == p])
+        shards.append([st.candidates(j) for j in range(4)])
+    for j in range(4):
+        m_ids, m_d = O.merge_shards([s[j] for s in shards], K)
+        w_ids, w_d = O.topk_exact(X, ids, Q[j], K)
+        assert np.array_equal(m_ids, w_ids) and np.array_equal(m_d.view(np.uint64), w_d.view(np.uint64))

@@ -78,7 +78,7 @@ def _worker(rank, world, port, out_dir):
     try:
         from oracle import cosine_topk as O
         from outline_rag_b200.sharded import ShardedIndex, shard_of
-        from outline_rag_b200.synth import Synth
+        from orx_testkit.synth import Synth
         syn = Synth(64)
         n, k = 1500, 12
         X = syn.table(n)
@@ -114,7 +114,7 @@ def _free_port():
 
 def test_two_rank_sharded_search_equals_single_table(tmp_path):
     from oracle import cosine_topk as O
-    from outline_rag_b200.synth import Synth
+    from orx_testkit.synth import Synth
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     syn = Synth(64)

@@ -56,7 +56,7 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{rank}"))
     try:
         from outline_rag_b200.sharded import ShardedIndex
-        from outline_rag_b200.synth import Synth
+        from orx_testkit.synth import Synth
         syn = Synth(1024)
         n = 30000
         X = syn.table(n)
@@ -96,7 +96,7 @@ def test_two_gpus_p2p_and_nccl_equal_the_oracle(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import torch.multiprocessing as mp
-    from outline_rag_b200.synth import Synth
+    from orx_testkit.synth import Synth
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     syn = Synth(1024)

@@ -4,7 +4,7 @@ by regenerating sampled rows on the host)."""
 import numpy as np
 import pytest
 
-from outline_rag_b200.synth import Synth, doc_chunk_counts, default_centres
+from orx_testkit.synth import Synth, doc_chunk_counts, default_centres
 
 
 def test_rows_are_unit_norm_and_reproducible(synth100k):
@@ -39,10 +39,26 @@ def test_doc_chunk_counts():
     assert default_centres(100_000) == 1024 and default_centres(1_000_000) == 16384
 
 
+def test_c_host_generator_is_bit_identical(synth100k):
+    """oracle/synth_host.c (what the CPU arm of bench.py and the 1M-row tests build their tables with) produces
+    the same bits as the NumPy generator: mean, centres, arbitrary rows, contiguous tables, queries."""
+    from oracle.synth_host import FastSynth
+    fast = FastSynth(synth100k.n_centres)
+    assert np.array_equal(fast.mean.view(np.uint32), synth100k.mean.view(np.uint32))
+    assert np.array_equal(fast.centres.view(np.uint32), synth100k.centres.view(np.uint32))
+    assert np.array_equal(fast.table(2500, start=77).view(np.uint32), synth100k.table(2500, start=77).view(np.uint32))
+    idx = np.array([5, 99_999_999, 123, 2**40 + 17], np.uint64)
+    assert np.array_equal(fast.rows(idx).view(np.uint32), synth100k.rows(idx).view(np.uint32))
+    qa, aa = fast.queries(5, 100_000)
+    qb, ab = synth100k.queries(5, 100_000)
+    assert np.array_equal(qa.view(np.uint32), qb.view(np.uint32)) and np.array_equal(aa, ab)
+    assert FastSynth(16384, threads=3).table(7, start=9_999_990).shape == (7, 1024)
+
+
 @pytest.mark.gpu
 def test_device_generator_is_bit_identical(synth100k):
     import torch
-    from outline_rag_b200 import synth_rows_device
+    from orx_testkit.device import synth_rows_device
     dev = synth_rows_device(0, synth100k.seed, synth100k.n_centres, 1000, 4096).cpu().numpy()
     host = synth100k.table(4096, start=1000)
     assert np.array_equal(dev.view(np.uint32), host.view(np.uint32))

@@ -24,7 +24,7 @@ def main():
     import torch
     import outline_rag_b200 as orx
     from bench import build_table
-    from outline_rag_b200.synth import Synth, default_centres
+    from orx_testkit.synth import Synth, default_centres
 
     from bench import measured_peaks
     hbm_peak, _, peak_src = measured_peaks()

@@ -16,7 +16,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import outline_rag_b200 as orx                                   # noqa: E402
 from bench import build_table                                    # noqa: E402
-from outline_rag_b200.synth import Synth, default_centres        # noqa: E402
+from orx_testkit.synth import Synth, default_centres        # noqa: E402
 
 
 class NoEmb:                                                     # queries arrive as vectors

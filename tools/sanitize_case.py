@@ -12,7 +12,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import outline_rag_b200 as orx                      # noqa: E402
 from oracle import cosine_topk as O                 # noqa: E402
-from outline_rag_b200.synth import Synth            # noqa: E402
+from orx_testkit.synth import Synth            # noqa: E402
 from tests._helpers import stored_bf16_rows         # noqa: E402
 
 syn = Synth(64)
