@@ -9,12 +9,13 @@
  * Conventions: return 0 = OK, negative = error (message via orx_last_error(),
  * thread-local).  The caller owns every buffer it passes; the library owns all
  * device memory.  Pointer arguments documented "host or device" are classified
- * with cudaPointerGetAttributes.  One orx_index lives on ONE GPU (one process per
- * GPU; row-sharding across GPUs is done above this API with torch.distributed,
- * see outline_rag_b200/sharded.py).  Calls on one index are serialised
- * internally (stream order = call order, so a search issued after an upsert sees
- * it: at least as consistent as the reference's separate delete / insert
- * transactions, app/rag.py:231-235).
+ * with cudaPointerGetAttributes.  An orx_index lives on ONE GPU (orx_create) or is
+ * a row-sharded table over several GPUs driven by one process (orx_create_multi);
+ * both kinds answer the same calls.  One process PER GPU (torchrun ranks,
+ * outline_rag_b200/sharded.py) uses orx_shard_* / orx_search_sharded instead.
+ * Calls on one index are serialised internally (stream order = call order, so a
+ * search issued after an upsert sees it: at least as consistent as the
+ * reference's separate delete / insert transactions, app/rag.py:231-235).
  */
 #ifndef ORX_H
 #define ORX_H
@@ -67,6 +68,20 @@ typedef struct orx_stats {
  * DDL `embedding vector(1024)` (app/database.py:118-131).  dim must be ORX_DIM. */
 int orx_create(orx_index **out, int dim, int dtype, uint64_t capacity_rows, int device);
 void orx_destroy(orx_index *idx);
+
+/* The same table ROW-SHARDED over the GPUs `devices[0..n_devices)` of one NVSwitch box, owned by ONE process -- what
+ * a uvicorn worker of the reference (app/entrypoint.sh:16, one `rag.vector_store` per process, app/rag.py:28) needs
+ * to put a table larger than one GPU, or the bandwidth of eight, behind the same object.
+ * Rows are placed by mix64(id) mod n_devices.  Every call of this header works on the returned handle: upsert /
+ * delete route rows to their shards; orx_search runs all shards concurrently (one launcher thread per GPU), every
+ * GPU's finalize kernel pushes its k candidates per query into the first GPU's gather buffer with peer stores over
+ * NVLink and that GPU merges them -- no collective library, no host round trip before the merged answer.  capacity_rows
+ * is the total.  A device may be listed more than once (several shards on one GPU: tests).  Device-resident query
+ * or output buffers must live on devices[0].  Not available on a multi-GPU handle: orx_set_stream, orx_filter_*
+ * handles (orx_search_filtered works), orx_shard_*. */
+int orx_create_multi(orx_index **out, int dim, int dtype, uint64_t capacity_rows,
+                     const int *devices, int n_devices);
+int orx_shard_count(const orx_index *idx);      /* 1 for orx_create, n_devices for orx_create_multi */
 
 /* Kernels are launched on this CUDA stream (a cudaStream_t; NULL = legacy default
  * stream).  Python hands over torch's current stream so torch.cuda.Event sees them. */

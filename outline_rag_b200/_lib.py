@@ -73,6 +73,8 @@ class OrxStats(C.Structure):
 _vp = C.c_void_p
 SIGNATURES = {
     "orx_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint64, C.c_int]),
+    "orx_create_multi": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_int), C.c_int]),
+    "orx_shard_count": (C.c_int, [_vp]),
     "orx_destroy": (None, [_vp]),
     "orx_set_stream": (C.c_int, [_vp, _vp]),
     "orx_size": (C.c_uint64, [_vp]),

@@ -60,30 +60,57 @@ __global__ void flags_from_prep_kernel(const QueryPrep *__restrict__ prep, int n
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < nq) flags[j] = (prep[j].nonfinite ? 2 : 0) | (prep[j].zero ? 4 : 0);
 }
+__global__ void fill_flags_kernel(int *__restrict__ flags, int nq, int value) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < nq) flags[j] = value;
+}
+void launch_fill_flags(int *flags, int nq, int value, cudaStream_t st) {
+    if (nq > 0) fill_flags_kernel<<<(nq + 127) / 128, 128, 0, st>>>(flags, nq, value);
+}
 void launch_flags_from_prep(const QueryPrep *prep, int nq, int *flags, cudaStream_t st) {
     if (nq > 0) flags_from_prep_kernel<<<(nq + 127) / 128, 128, 0, st>>>(prep, nq, flags);
 }
 
 // ------------------------------------------------------------------- finalize
 // One CTA of 16 warps per query (512 threads: the binary64 rescore needs ~100 registers).
-//   1. every warp folds its share of the per-CTA candidate lists into a register-resident sorted
-//      top-K (K = 32*S), then a 4-level tree merge through shared memory leaves the query's top-K;
-//   2. canonical binary64 rescore, one warp per candidate (all K in flight at once);
+//   1. the query's top-K candidates by fast score (K = 32*S) out of the scan's per-CTA lists:
+//      1a sorted lists (GEMV scan): the K-th largest list HEAD is a lower bound of the global K-th best key and only
+//         the K lists whose head reaches it can hold keys above it -- K coalesced list reads, one round of loads;
+//      1c unsorted lists that fit shared memory (tcgen05 scan): bitonic sort;  1b generic: warp top-K + tree merge;
+//   2. canonical binary64 rescore, one warp per candidate, the query staged in shared memory, the next round's rows
+//      prefetched into L2 while this round's are summed;
 //   3. rank by (distance ASC, NaN last, id ASC) by counting;
-//   4. completeness proof -> flag (bit 0: unproven, bit 1: non-finite query, bit 2: zero query).
+//   4. completeness proof -> flag (bit 0: unproven, bit 1: non-finite query, bit 2: zero query);
+//   5. results go where the search wants them -- caller / mapped host arrays, or (row-sharded search) straight into
+//      the gather buffers of the peer GPUs with P2P stores; the search's last CTA raises the arrival words / the
+//      host's completion word (internal.h PublishArgs / DoneArgs), so no publish kernel and no stream sync follow.
 constexpr int FIN_THREADS = 512;
 constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int FIN_SURV = 256;          // survivors of the head-threshold filter (fast path)
 constexpr int FIN_SORT_MAX = 2048;     // keys the shared-memory bitonic sort takes (unsorted-list path)
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// canonical binary64 dot of a stored row with the query held in shared memory (same tree as warp_canon_dot)
+template <typename T>
+__device__ __forceinline__ double warp_canon_dot_sq(const T *row, const float *s_q, int lane) {
+    double p[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int e = lane + 32 * j;
+        p[j] = __dmul_rn((double)row_elem<T>(row, e), (double)s_q[e]);
+    }
+    return bcast_lane0(canon_tree_1024(p));
+}
 
 template <typename T, int S>
 __global__ void __launch_bounds__(FIN_THREADS)
 finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                 const orx_id *__restrict__ row_ids, const float *__restrict__ q_all,
                 const QueryPrep *__restrict__ prep, const uint64_t *__restrict__ partial_all,
-                int nparts, int k, uint32_t n_rows, double eps, orx_id *__restrict__ out_ids,
-                double *__restrict__ out_dist, int *__restrict__ out_counts,
-                int *__restrict__ out_flags, const float *__restrict__ floor_all, int sorted_lists) {
+                int nparts, int k, uint32_t n_rows, double eps, const ResultOut out, int q_base,
+                const PublishArgs pub, const DoneArgs done, const float *__restrict__ floor_all,
+                int sorted_lists) {
     constexpr int K = 32 * S;
     __shared__ uint64_t s_keys[FIN_WARPS][K];
     __shared__ double s_dist[K];
@@ -104,11 +131,10 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     __shared__ uint64_t s_surv[FIN_SURV];
     __shared__ uint64_t s_thresh;
     __shared__ int s_nsurv;
+    __shared__ int s_sel[K];
     uint64_t *s_flat = &s_keys[0][0];                   // FIN_WARPS*K >= 512 words of scratch
     bool fast = sorted_lists && nparts >= K && nparts <= FIN_THREADS;
     if (fast) {
-        // 1a (sorted lists, GEMV scan): the K-th largest list HEAD is a lower bound of the global
-        //     K-th best key, so only keys >= it can matter -- typically a few dozen of nparts*K.
         if (threadIdx.x == 0) {
             s_nsurv = 0;
             s_thresh = 0ull;
@@ -116,35 +142,52 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         const uint64_t head = threadIdx.x < nparts ? partial[(size_t)threadIdx.x * K] : 0ull;
         s_flat[threadIdx.x] = head;
         __syncthreads();
-        if (threadIdx.x < nparts) {
+        if (threadIdx.x < nparts && head != 0ull) {
             int rank = 0;
             for (int i = 0; i < nparts; ++i) rank += (s_flat[i] > head);
-            if (rank == K - 1) s_thresh = head;         // heads are distinct rows (or 0: then rank >= #nonzero)
+            if (rank < K) s_sel[rank] = threadIdx.x;    // heads are distinct rows: ranks 0..K-1 are taken exactly once
+            if (rank == K - 1) s_thresh = head;
         }
         __syncthreads();
         const uint64_t T = s_thresh;
-        const int total = nparts * K;
-        for (int i = threadIdx.x; i < total; i += FIN_THREADS) {
-            const uint64_t key = partial[i];
-            if (key >= T && key != 0ull) {
-                const int pos = atomicAdd(&s_nsurv, 1);
-                if (pos < FIN_SURV) s_surv[pos] = key;
-            }
-        }
-        __syncthreads();
-        const int ns = s_nsurv;
-        if (T == 0ull || ns > FIN_SURV) fast = false;   // fewer than K non-empty lists, or a flood of ties
+        if (T == 0ull) fast = false;                    // fewer than K non-empty lists
         else {
-            __syncthreads();
-            if (threadIdx.x < K) s_flat[threadIdx.x] = 0ull;
-            __syncthreads();
-            if (threadIdx.x < ns) {
-                const uint64_t mine = s_surv[threadIdx.x];
-                int rank = 0;
-                for (int i = 0; i < ns; ++i) rank += (s_surv[i] > mine);
-                if (rank < K) s_flat[rank] = mine;
+            // every key >= T lives in one of the K selected lists; each warp reads whole lists, coalesced
+            constexpr int LISTS_PER_WARP = (K + FIN_WARPS - 1) / FIN_WARPS;
+#pragma unroll 2
+            for (int u = 0; u < LISTS_PER_WARP; ++u) {
+                const int li = warp + u * FIN_WARPS;
+                const uint64_t *src = partial + (size_t)s_sel[li < K ? li : 0] * K;
+                uint64_t mine[S];
+#pragma unroll
+                for (int sl = 0; sl < S; ++sl) mine[sl] = li < K ? src[sl * 32 + lane] : 0ull;
+#pragma unroll
+                for (int sl = 0; sl < S; ++sl) {
+                    const bool keep = mine[sl] >= T && mine[sl] != 0ull;
+                    const unsigned m = __ballot_sync(FULL_MASK, keep);
+                    if (m == 0u) continue;
+                    int base = 0;
+                    if (lane == 0) base = atomicAdd(&s_nsurv, __popc(m));
+                    base = __shfl_sync(FULL_MASK, base, 0);
+                    const int pos = base + __popc(m & ((1u << lane) - 1u));
+                    if (keep && pos < FIN_SURV) s_surv[pos] = mine[sl];
+                }
             }
             __syncthreads();
+            const int ns = s_nsurv;
+            if (ns > FIN_SURV) fast = false;            // a flood of ties
+            else {
+                __syncthreads();
+                if (threadIdx.x < K) s_flat[threadIdx.x] = 0ull;
+                __syncthreads();
+                if (threadIdx.x < ns) {
+                    const uint64_t me = s_surv[threadIdx.x];
+                    int rank = 0;
+                    for (int i = 0; i < ns; ++i) rank += (s_surv[i] > me);
+                    if (rank < K) s_flat[rank] = me;
+                }
+                __syncthreads();
+            }
         }
     }
     __shared__ uint64_t s_all[FIN_SORT_MAX];
@@ -204,7 +247,10 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     //    margin below the k-th best COARSE score cannot reach the top-k (same argument as the scan's
     //    running threshold), so they are not rescored; the proof below accounts for them through `cut`.
     __shared__ unsigned char s_ok[K];
+    float *s_q = reinterpret_cast<float *>(s_all);          // the bitonic scratch is free now: stage the query (4 KB)
     const float *q = q_all + (size_t)qi * ORX_DIM;
+    __syncthreads();
+    for (int e = threadIdx.x; e < ORX_DIM; e += FIN_THREADS) s_q[e] = q[e];
     const double n2q = prep[qi].n2q;
     float cut = __int_as_float(0xff800000);               // -inf: nothing is cut
     if (floor_all != nullptr) {
@@ -216,10 +262,19 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         const uint32_t ok_ord = kth < K ? key_ord(s_cand[kth]) : 0u;
         if (ok_ord != 0u) cut = ord_to_float(ok_ord) - (float)(2.0 * eps + 1e-6);
     }
+    auto skipped = [&](uint64_t key) {
+        return key == 0ull || (key_ord(key) != ORD_ALWAYS && ord_to_float(key_ord(key)) <= cut);
+    };
+    __syncthreads();
     for (int c = warp; c < K; c += FIN_WARPS) {
         const uint64_t key = s_cand[c];
-        const bool skip = key == 0ull || (key_ord(key) != ORD_ALWAYS && ord_to_float(key_ord(key)) <= cut);
-        if (skip) {                           // empty or cut: sorts after everything, never output
+        // the row this warp takes in the NEXT round: pull its 32 lines towards L2 now (one line per lane)
+        if (c + FIN_WARPS < K) {
+            const uint64_t nk = s_cand[c + FIN_WARPS];
+            if (!skipped(nk))
+                prefetch_l2(reinterpret_cast<const char *>(table + (size_t)key_row(nk) * ORX_DIM) + lane * (ORX_DIM * sizeof(T) / 32));
+        }
+        if (skipped(key)) {                   // empty or cut: sorts after everything, never output
             if (lane == 0) {
                 s_ok[c] = 0;
                 s_dist[c] = __longlong_as_double(0x7ff8000000000000ll);
@@ -231,7 +286,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         const uint32_t row = key_row(key);
         const double n2x = n2[row];                       // issued before the row itself: one DRAM round trip
         const orx_id id = row_ids[row];
-        const double dot = warp_canon_dot<T>(table + (size_t)row * ORX_DIM, q, lane);
+        const double dot = warp_canon_dot_sq<T>(table + (size_t)row * ORX_DIM, s_q, lane);
         if (lane == 0) {
             s_ok[c] = 1;
             s_dist[c] = canon_dist(dot, n2x, n2q);
@@ -242,8 +297,10 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     }
     __syncthreads();
 
-    // 3. order by (distance ASC, NaN last, id ASC): rank by counting
+    // 3. order by (distance ASC, NaN last, id ASC): rank by counting; 5. write where the search wants the results
     const int t = threadIdx.x;
+    const size_t qo = (size_t)(q_base + qi);
+    const int n_out = pub.n_targets > 0 ? pub.n_targets : 1;
     const int count = min(k, s_valid);
     if (t < K && s_ok[t]) {
         int rank = 0;
@@ -252,16 +309,26 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         for (int c = 0; c < K; ++c)
             rank += (c != t && s_ok[c] && sorts_before(s_dist[c], s_hi[c], s_lo[c], d, hi, lo));
         if (rank < k) {
-            out_ids[(size_t)qi * k + rank].hi = hi;
-            out_ids[(size_t)qi * k + rank].lo = lo;
-            out_dist[(size_t)qi * k + rank] = d;
+            for (int o = 0; o < n_out; ++o) {
+                char *b = pub.n_targets > 0 ? pub.slot[o] : nullptr;
+                orx_id *oi = b ? reinterpret_cast<orx_id *>(b) : out.ids;
+                double *od = b ? reinterpret_cast<double *>(b + pub.dist_off) : out.dist;
+                oi[qo * k + rank].hi = hi;
+                oi[qo * k + rank].lo = lo;
+                od[qo * k + rank] = d;
+            }
         }
         if (rank == count - 1) s_kth = d;
     }
     if (t >= count && t < k) {
-        out_ids[(size_t)qi * k + t].hi = 0ull;
-        out_ids[(size_t)qi * k + t].lo = 0ull;
-        out_dist[(size_t)qi * k + t] = __longlong_as_double(0x7ff8000000000000ll);
+        for (int o = 0; o < n_out; ++o) {
+            char *b = pub.n_targets > 0 ? pub.slot[o] : nullptr;
+            orx_id *oi = b ? reinterpret_cast<orx_id *>(b) : out.ids;
+            double *od = b ? reinterpret_cast<double *>(b + pub.dist_off) : out.dist;
+            oi[qo * k + t].hi = 0ull;
+            oi[qo * k + t].lo = 0ull;
+            od[qo * k + t] = __longlong_as_double(0x7ff8000000000000ll);
+        }
     }
     __syncthreads();
 
@@ -270,7 +337,6 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     //    <= the merged list's K-th.  tcgen05 scan (floor_all != null): the lists hold every row
     //    above the CTA's running threshold; outside rows are <= max(final thresholds, merged K-th).
     if (t == 0) {
-        out_counts[qi] = count;
         int flag = 1;
         const bool coarse = floor_all != nullptr;
         if (!coarse && n_rows <= (uint32_t)K) {
@@ -298,19 +364,42 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                 flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
             }
         }
-        out_flags[qi] = flag | (prep[qi].nonfinite ? 2 : 0) | (prep[qi].zero ? 4 : 0);
+        flag |= (prep[qi].nonfinite ? 2 : 0) | (prep[qi].zero ? 4 : 0);
+        for (int o = 0; o < n_out; ++o) {
+            char *b = pub.n_targets > 0 ? pub.slot[o] : nullptr;
+            int *oc = b ? reinterpret_cast<int *>(b + pub.counts_off) : out.counts;
+            int *of = b ? reinterpret_cast<int *>(b + pub.flags_off) : out.flags;
+            oc[qo] = count;
+            of[qo] = flag;
+        }
+    }
+
+    // 5. completion: every thread's result stores are performed system-wide before this CTA counts itself; the
+    //    search's last CTA raises the arrival words on the targets / the host's completion word.
+    if (done.counter != nullptr) {
+        __threadfence_system();
+        __syncthreads();
+        if (t == 0) {
+            const unsigned int old = atomicAdd(done.counter, 1u);
+            if (old + 1u == done.total) {
+                *done.counter = 0u;
+                __threadfence_system();
+                for (int o = 0; o < pub.n_targets; ++o) *reinterpret_cast<volatile uint32_t *>(pub.flag[o]) = pub.seq;
+                if (done.done_host != nullptr) *reinterpret_cast<volatile uint32_t *>(done.done_host) = done.token;
+            }
+        }
     }
 }
 
 template <typename T>
 static void launch_finalize_t(const void *table, const double *n2, const orx_id *row_ids, const float *q,
                               const QueryPrep *prep, const uint64_t *partial, int nparts, int slots, int nq,
-                              int k, uint32_t n_rows, double eps, orx_id *out_ids, double *out_dist,
-                              int *out_counts, int *out_flags, cudaStream_t st, const float *floor) {
+                              int k, uint32_t n_rows, double eps, const ResultOut &out, int q_base,
+                              const PublishArgs &pub, const DoneArgs &done, cudaStream_t st, const float *floor) {
     const T *tab = static_cast<const T *>(table);
 #define ORX_FIN(S_)                                                                                          \
     finalize_kernel<T, S_><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows, eps, \
-                                                       out_ids, out_dist, out_counts, out_flags, floor, floor == nullptr)
+                                                       out, q_base, pub, done, floor, floor == nullptr)
     switch (slots) {
         case 1: ORX_FIN(1); break;
         case 2: ORX_FIN(2); break;
@@ -322,16 +411,22 @@ static void launch_finalize_t(const void *table, const double *n2, const orx_id 
 
 void launch_finalize(int dtype, const void *table, const double *n2, const orx_id *row_ids,
                      const float *q, const QueryPrep *prep, const uint64_t *partial, int nparts,
-                     int slots, int nq, int k, uint32_t n_rows, double eps, orx_id *out_ids,
-                     double *out_dist, int *out_counts, int *out_flags, cudaStream_t st, const float *floor) {
+                     int slots, int nq, int k, uint32_t n_rows, double eps, const ResultOut &out, int q_base,
+                     const PublishArgs &pub, const DoneArgs &done, cudaStream_t st, const float *floor) {
     if (nq <= 0) return;
     if (dtype == ORX_DTYPE_F32)
         launch_finalize_t<float>(table, n2, row_ids, q, prep, partial, nparts, slots, nq, k, n_rows, eps,
-                                 out_ids, out_dist, out_counts, out_flags, st, floor);
+                                 out, q_base, pub, done, st, floor);
     else
         launch_finalize_t<__nv_bfloat16>(table, n2, row_ids, q, prep, partial, nparts, slots, nq, k, n_rows,
-                                         eps, out_ids, out_dist, out_counts, out_flags, st, floor);
+                                         eps, out, q_base, pub, done, st, floor);
 }
+
+__global__ void signal_done_kernel(DoneArgs done) {
+    __threadfence_system();
+    if (done.done_host != nullptr) *reinterpret_cast<volatile uint32_t *>(done.done_host) = done.token;
+}
+void launch_signal_done(const DoneArgs &done, cudaStream_t st) { signal_done_kernel<<<1, 1, 0, st>>>(done); }
 
 // ----------------------------------------------------------------- merge_topk
 // The on-device step after the allgather of the row-sharded path: n_lists shard results

@@ -5,7 +5,12 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -60,6 +65,16 @@ bool is_device_ptr(const void *p) {
         return false;
     }
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+// the device a device pointer lives on, or -1 for host memory
+int ptr_device(const void *p) {
+    if (!p) return -1;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) ? at.device : -1;
 }
 
 size_t elem_size(int dtype) { return dtype == ORX_DTYPE_F32 ? 4 : 2; }
@@ -124,8 +139,9 @@ struct PinBuf {
 constexpr int XQ_MAX = 1024;                         // queries per exchange round (larger batches are chunked)
 constexpr size_t XFLAG_STRIDE = 128;                 // one arrival word per 128 bytes
 
-struct Exchange {   // peer-memory exchange state of one rank (orx_shard_*)
+struct Exchange {   // peer-memory exchange state of one rank (orx_shard_*) or of one shard of a one-process group
     int world = 0, rank = 0;
+    int n_targets = 0;                               // gather buffers my block is pushed into: every rank's, or the group root's
     size_t slot_bytes = 0;                           // capacity of one slot
     size_t set_bytes = 0;                            // world slots
     size_t flags_off = 0;                            // offset of the arrival words (2 sets x world x 128 B)
@@ -168,7 +184,11 @@ struct orx_index {
     PinBuf<orx_id> h_ids;
     PinBuf<double> h_dist;
     PinBuf<int> h_counts, h_flags, h_myflags, h_redo;
+    PinBuf<uint32_t> h_done;            // [0] completion word the last CTA of a search writes (host polls it), [1] error word
+    DevBuf<unsigned int> d_counters;    // [0] finalize CTAs, [1] merge CTAs of the search in flight (0 between searches)
+    uint32_t token = 0;                 // last completion token handed out (never 0)
     struct Exchange *xchg = nullptr;     // peer-memory exchange of the row-sharded search (orx_shard_*)
+    struct Group *group = nullptr;       // non-null: this handle is a multi-GPU group (orx_create_multi); shard fields unused
     // filtered search: eligibility bitmap (one bit per row) for the filtered scan
     DevBuf<uint32_t> allow_bits;
     PinBuf<uint32_t> h_allow_bits;
@@ -199,6 +219,10 @@ struct orx_filter {     // a reusable resolved predicate (orx_filter_create / or
     uint64_t generation = 0;
     bool resolved = false;
 };
+
+#define ORX_GROUP_TYPES
+#include "group.inl"
+#undef ORX_GROUP_TYPES
 
 namespace {
 
@@ -247,11 +271,19 @@ int grow_table(orx_index *ix, uint64_t need) {
         return fail(ORX_ERR_CAPACITY, "cannot grow table to %llu rows: %s", (unsigned long long)cap,
                     cudaGetErrorString(e));
     }
-    CK(cudaMemcpyAsync(t, ix->table, ix->n_live * rb, cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaMemcpyAsync(s, ix->scale, ix->n_live * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaMemcpyAsync(n, ix->n2, ix->n_live * sizeof(double), cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaMemcpyAsync(r, ix->row_ids, ix->n_live * sizeof(orx_id), cudaMemcpyDeviceToDevice, ix->stream));
-    CK(cudaStreamSynchronize(ix->stream));
+    e = cudaMemcpyAsync(t, ix->table, ix->n_live * rb, cudaMemcpyDeviceToDevice, ix->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s, ix->scale, ix->n_live * sizeof(float), cudaMemcpyDeviceToDevice, ix->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(n, ix->n2, ix->n_live * sizeof(double), cudaMemcpyDeviceToDevice, ix->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(r, ix->row_ids, ix->n_live * sizeof(orx_id), cudaMemcpyDeviceToDevice, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    if (e != cudaSuccess) {                 // the old table stays in place and valid
+        cudaGetLastError();
+        cudaFree(t);
+        cudaFree(s);
+        cudaFree(n);
+        cudaFree(r);
+        return fail(ORX_ERR_CUDA, "copying the table to its grown allocation failed: %s", cudaGetErrorString(e));
+    }
     cudaFree(ix->table);
     cudaFree(ix->scale);
     cudaFree(ix->n2);
@@ -262,6 +294,120 @@ int grow_table(orx_index *ix, uint64_t need) {
     ix->row_ids = r;
     ix->capacity = cap;
     if (ix->umma) orx::umma_plan_invalidate(ix->umma);
+    return ORX_OK;
+}
+
+int group_upsert(Group *g, const orx_id *ids, const float *vecs, uint64_t n);
+
+// ---------------------------------------------------------------- upsert
+// validate (pgvector's element check over the WHOLE batch) -> commit, stream-ordered: the commit kernels read the
+// validation flag on the device and write nothing when it is set, so a batch of up to STAGE_ROWS rows needs ONE host
+// synchronisation.  Host state (id -> row map, live row count) is published only after the device work of a chunk
+// has succeeded: an error in between leaves ids mapped to nothing new and the live rows untouched.
+int upsert_locked(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t n, bool validate) {
+    cudaStream_t st = ix->stream;
+    const bool on_dev = is_device_ptr(vecs);
+    const uint64_t chunk = std::min<uint64_t>(n, STAGE_ROWS);
+    CK(ix->d_flag.ensure(1));
+    CK(ix->h_flag.ensure(1));
+    if (!on_dev) CK(ix->stage.ensure(chunk * ORX_DIM));
+    const bool single = n <= chunk;           // one chunk: staged once, validated and committed back to back
+
+    CK(cudaMemsetAsync(ix->d_flag.p, 0, sizeof(int), st));
+    if (validate && !single) {
+        // several chunks: the whole batch is checked before anything is written
+        for (uint64_t s = 0; s < n; s += chunk) {
+            const uint64_t m = std::min(chunk, n - s);
+            const float *src = vecs + s * ORX_DIM;
+            if (!on_dev) {
+                CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+                src = ix->stage.p;
+            }
+            orx::launch_validate_rows(src, m, ix->d_flag.p, st);
+            ix->stats.kernel_launches += 1;
+        }
+        CK(cudaMemcpyAsync(ix->h_flag.p, ix->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
+    }
+
+    // room for every id that is new (existing id -> its row, new id -> append; last duplicate wins)
+    uint64_t n_new = 0;
+    {
+        std::unordered_map<orx_id, int, IdHash, IdEq> seen;
+        if (n > 1) seen.reserve(n);
+        for (uint64_t i = 0; i < n; ++i)
+            if (ix->map.find(ids[i]) == ix->map.end() && seen.emplace(ids[i], 1).second) ++n_new;
+    }
+    int rc = grow_table(ix, ix->n_live + n_new);
+    if (rc != ORX_OK) return rc;
+
+    CK(ix->d_src_idx.ensure(chunk));
+    CK(ix->d_dst_row.ensure(chunk));
+    CK(ix->d_ids.ensure(chunk));
+    CK(ix->h_u32a.ensure(chunk));
+    CK(ix->h_u32b.ensure(chunk));
+    std::unordered_map<orx_id, uint32_t, IdHash, IdEq> pending;      // ids new in this chunk -> row (published after the sync)
+    std::unordered_map<uint32_t, uint32_t> slot_of_row;              // dst row -> plan slot
+    for (uint64_t s = 0; s < n; s += chunk) {
+        const uint64_t m = std::min(chunk, n - s);
+        pending.clear();
+        slot_of_row.clear();
+        uint32_t np = 0;
+        uint64_t next_row = ix->n_live;
+        for (uint64_t i = 0; i < m; ++i) {
+            const orx_id id = ids[s + i];
+            uint32_t row;
+            auto it = ix->map.find(id);
+            if (it != ix->map.end()) row = it->second;
+            else {
+                auto pit = pending.find(id);
+                if (pit != pending.end()) row = pit->second;
+                else {
+                    row = (uint32_t)next_row++;
+                    pending.emplace(id, row);
+                }
+            }
+            auto ps = slot_of_row.find(row);
+            if (ps != slot_of_row.end()) ix->h_u32a.p[ps->second] = (uint32_t)i;     // the later source row wins
+            else {
+                slot_of_row.emplace(row, np);
+                ix->h_u32a.p[np] = (uint32_t)i;
+                ix->h_u32b.p[np] = row;
+                ++np;
+            }
+        }
+        const float *src = vecs + s * ORX_DIM;
+        if (!on_dev) {
+            CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            src = ix->stage.p;
+        }
+        if (validate && single) {
+            orx::launch_validate_rows(src, m, ix->d_flag.p, st);
+            ix->stats.kernel_launches += 1;
+        }
+        CK(cudaMemcpyAsync(ix->d_src_idx.p, ix->h_u32a.p, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_dst_row.p, ix->h_u32b.p, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(ix->d_ids.p, ids + s, m * sizeof(orx_id), cudaMemcpyHostToDevice, st));
+        orx::launch_commit_rows(ix->dtype, src, ix->d_src_idx.p, ix->d_dst_row.p, ix->d_ids.p, np, ix->table,
+                                ix->scale, ix->n2, ix->row_ids, ix->d_flag.p, st);
+        ix->stats.kernel_launches += 1;
+        CK(cudaMemcpyAsync(ix->h_flag.p, ix->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));     // the ONE sync of a chunk: scratch + the caller's buffers are reusable after it
+        CK(cudaGetLastError());
+        if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
+        // ---- the device holds the rows: publish them
+        if (!pending.empty()) {
+            if (ix->host_row_ids.size() < next_row) ix->host_row_ids.resize(next_row);
+            for (const auto &kv : pending) {
+                ix->map.emplace(kv.first, kv.second);
+                ix->host_row_ids[kv.second] = kv.first;
+            }
+            ix->n_live = next_row;
+            ix->generation += 1;
+        }
+    }
     return ORX_OK;
 }
 
@@ -290,14 +436,19 @@ void harvest_scan_events(orx_index *ix) {       // stream is synchronised
     cudaGetLastError();
 }
 
-struct SearchOut {          // where the results of query j go (device pointers)
-    orx_id *ids;
-    double *dist;
-    int *counts;
+struct SearchCtx {          // where a search's results go and how its completion is signalled (internal.h)
+    orx::ResultOut out;
+    orx::PublishArgs pub;
+    orx::DoneArgs done;
 };
+SearchCtx plain_ctx(orx_id *ids, double *dist, int *counts, int *flags) {      // no publish, no completion word
+    SearchCtx c{};
+    c.out = orx::ResultOut{ids, dist, counts, flags};
+    return c;
+}
 
 int exhaustive_query(orx_index *ix, const float *q_src, int qi, int k, double dk, bool force_all,
-                     const SearchOut &out) {
+                     const orx::ResultOut &out) {
     // Collect every row that could sort at or before the current k-th candidate, rescore all of
     // them canonically, select the k best.  Always exact; cost grows with the number of near-ties.
     const uint32_t n_rows = (uint32_t)ix->n_live;
@@ -324,7 +475,7 @@ int exhaustive_query(orx_index *ix, const float *q_src, int qi, int k, double dk
     return ORX_OK;
 }
 
-int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const SearchOut &out, int *flags) {
+int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const SearchCtx &ctx) {
     const uint32_t n_rows = (uint32_t)ix->n_live;
     const int grid = orx::scan_gemv_grid(ix->device, n_rows);
     const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
@@ -339,9 +490,8 @@ int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const Se
                               slots, ix->partial.p, grid, ix->stream);
         if (e0 && e1) CK(cudaEventRecord(e1, ix->stream));
         orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)qa * ORX_DIM,
-                             ix->prep.p + qa, ix->partial.p, grid, slots, m, k, n_rows, eps,
-                             out.ids + (size_t)qa * k, out.dist + (size_t)qa * k, out.counts + qa,
-                             flags + qa, ix->stream);
+                             ix->prep.p + qa, ix->partial.p, grid, slots, m, k, n_rows, eps, ctx.out, qa, ctx.pub,
+                             ctx.done, ix->stream);
         ix->stats.kernel_launches += 2;
     }
     CK(cudaGetLastError());
@@ -352,7 +502,8 @@ constexpr uint32_t FILTER_SCAN_MIN_ROWS = 4096;   // eligible rows from which th
 constexpr int ZERO_COPY_MAX_Q = 16;     // query batches up to this size are read by the prep kernel over PCIe
 
 // ---- query staging: *q_src is what the rescoring kernels read (device memory); launches prep
-int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_src) {
+//      src_pinned: `queries` is mapped pinned host memory every device can read (a group stages the batch once)
+int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_src, bool src_pinned = false) {
     cudaStream_t st = ix->stream;
     // the tcgen05 scan reads query tiles of 128 rows (256 per CTA pair): keep the buffers padded (and the pad zeroed) so
     // its TMA never touches an out-of-range row (measured: mostly-out-of-range query boxes cost ~40 %)
@@ -364,18 +515,29 @@ int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_s
         CK(cudaMemsetAsync(ix->qhat.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(float), st));
         CK(cudaMemsetAsync(ix->qhat16.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(__nv_bfloat16), st));
     }
-    if (is_device_ptr(queries)) {
+    const int qdev = ptr_device(queries);
+    if (qdev == ix->device) {
         *q_src = queries;
         orx::launch_prep_queries(queries, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+    } else if (qdev >= 0) {
+        // the batch lives on ANOTHER GPU (a group's shards all receive the root's pointer): the prep kernel reads it
+        // over NVLink once and leaves a local copy for the rescoring kernels
+        CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
+        *q_src = ix->q_dev.p;
+        orx::launch_prep_queries(queries, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
     } else {
         CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
-        CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
-        memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
+        const float *pinned = queries;
+        if (!src_pinned) {
+            CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
+            memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
+            pinned = ix->h_q.p;
+        }
         *q_src = ix->q_dev.p;
         if (nq <= ZERO_COPY_MAX_Q) {
-            orx::launch_prep_queries(ix->h_q.p, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+            orx::launch_prep_queries(pinned, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
         } else {
-            CK(cudaMemcpyAsync(ix->q_dev.p, ix->h_q.p, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            CK(cudaMemcpyAsync(ix->q_dev.p, pinned, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
             orx::launch_prep_queries(ix->q_dev.p, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
         }
     }
@@ -384,32 +546,71 @@ int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_s
 }
 
 // ---- the scan + finalize of all nq queries (tcgen05 for batches, GEMV otherwise); *path = 1 / 2
-int scan_pass(orx_index *ix, const float *q_src, int nq, int k, const SearchOut &out, int *flags, int *path) {
+int scan_pass(orx_index *ix, const float *q_src, int nq, int k, const SearchCtx &ctx, int *path) {
     const uint32_t n_rows = (uint32_t)ix->n_live;
     if (ix->umma && k <= 32 && orx::umma_should_use(ix->umma, nq, n_rows)) {
         *path = 2;
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
-                                  q_src, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, out.ids, out.dist,
-                                  out.counts, flags, ix->stream, &ix->stats.kernel_launches, e0, e1);
+                                  q_src, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, ctx.out, ctx.pub, ctx.done,
+                                  ix->stream, &ix->stats.kernel_launches, e0, e1);
         if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
         return ORX_OK;
     }
     *path = 1;
-    return gemv_pass(ix, q_src, 0, nq, k, out, flags);
+    return gemv_pass(ix, q_src, 0, nq, k, ctx);
+}
+
+// ---- completion of the search whose last kernel writes `token` into the mapped completion word: the host polls the
+//      word (a few ns per poll, visible ~1 us after the store) instead of cudaStreamSynchronize; the stream is queried
+//      now and then so that a failed launch or a dead kernel surfaces as an error instead of an endless spin.
+uint32_t next_token(orx_index *ix) {
+    if (++ix->token == 0) ++ix->token;
+    return ix->token;
+}
+int wait_done(orx_index *ix, uint32_t token) {
+    volatile uint32_t *w = ix->h_done.p;
+    for (uint64_t it = 0;; ++it) {
+        if (*w == token) return ORX_OK;
+        if ((it & 0x3FFu) == 0x3FFu) {
+            cudaError_t e = cudaStreamQuery(ix->stream);
+            if (e == cudaSuccess) {
+                if (*w == token) return ORX_OK;
+                return fail(ORX_ERR_CUDA, "search finished without signalling completion");
+            }
+            if (e != cudaErrorNotReady) return fail(ORX_ERR_CUDA, "search failed: %s", cudaGetErrorString(e));
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+    }
+}
+int ensure_signalling(orx_index *ix) {
+    if (!ix->h_done.p) {
+        CK(ix->h_done.ensure(2));
+        ix->h_done.p[0] = 0;
+        ix->h_done.p[1] = 0;
+    }
+    if (!ix->d_counters.p) {
+        CK(ix->d_counters.ensure(2));
+        CK(cudaMemsetAsync(ix->d_counters.p, 0, ix->d_counters.n * sizeof(unsigned int), ix->stream));
+    }
+    return ORX_OK;
 }
 
 // ---- re-answer the queries whose flag bit 0 (unproven) is set.  `flags` is where the kernels
 //      write (device or mapped host); hflags is a host-readable copy, refreshed here as needed.
-int resolve_unproven(orx_index *ix, const float *q_src, int nq, int k, const SearchOut &out, int *flags,
+int resolve_unproven(orx_index *ix, const float *q_src, int nq, int k, const orx::ResultOut &out,
                      int *hflags, int path, bool host_readable) {
+    int *flags = out.flags;
+    const SearchCtx ctx = plain_ctx(out.ids, out.dist, out.counts, out.flags);
     cudaStream_t st = ix->stream;
     // level 1: coarse tensor-core pass unproven -> exact fp32 scan for those queries
     if (path == 2) {
         for (int j = 0; j < nq; ++j) {
             if (!(hflags[j] & 1)) continue;
             ix->stats.fallback_gemv += 1;
-            int rc = gemv_pass(ix, q_src, j, 1, k, out, flags);
+            int rc = gemv_pass(ix, q_src, j, 1, k, ctx);
             if (rc != ORX_OK) return rc;
         }
         if (!host_readable) CK(cudaMemcpyAsync(hflags, flags, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -458,12 +659,14 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         CK(ix->h_counts.ensure(nq));
     }
     // host-side results are written by the kernels straight into mapped pinned memory
-    SearchOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                  out_on_dev ? out_counts : ix->h_counts.p};
     int *flags = ix->h_flags.p;
+    const orx::ResultOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                             out_on_dev ? out_counts : ix->h_counts.p, flags};
+    int rc = ensure_signalling(ix);
+    if (rc != ORX_OK) return rc;
 
     const float *q_src = nullptr;
-    int rc = stage_queries(ix, queries, nq, &q_src);
+    rc = stage_queries(ix, queries, nq, &q_src);
     if (rc != ORX_OK) return rc;
 
     const uint32_t n_rows = (uint32_t)ix->n_live;
@@ -490,9 +693,19 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         ix->stats.queries += nq;
         return ORX_OK;
     }
-    rc = scan_pass(ix, q_src, nq, k, out, flags, &path);
+    SearchCtx ctx{};
+    ctx.out = out;
+    const uint32_t token = next_token(ix);
+    ctx.done = orx::DoneArgs{ix->d_counters.p, (unsigned int)nq, ix->h_done.p, token};
+    rc = scan_pass(ix, q_src, nq, k, ctx, &path);
+    if (rc != ORX_OK) {
+        cudaStreamSynchronize(st);          // part of the chain may be in flight: drain it, forget its count
+        cudaMemsetAsync(ix->d_counters.p, 0, 2 * sizeof(unsigned int), st);
+        cudaGetLastError();
+        return rc;
+    }
+    rc = wait_done(ix, token);              // the last finalize CTA wrote the completion word; flags are on the host
     if (rc != ORX_OK) return rc;
-    CK(cudaStreamSynchronize(st));          // the only sync of the common path; flags are on the host now
 
     bool any_unproven = false;
     for (int j = 0; j < nq; ++j) {
@@ -500,7 +713,7 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
         any_unproven |= (flags[j] & 1) != 0;
     }
     if (any_unproven) {
-        rc = resolve_unproven(ix, q_src, nq, k, out, flags, flags, path, /*host_readable=*/!out_on_dev);
+        rc = resolve_unproven(ix, q_src, nq, k, out, flags, path, /*host_readable=*/!out_on_dev);
         if (rc != ORX_OK) return rc;
     }
     if (!out_on_dev) {
@@ -590,8 +803,9 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
         CK(ix->h_dist.ensure(nk));
         CK(ix->h_counts.ensure(nq));
     }
-    SearchOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                  out_on_dev ? out_counts : ix->h_counts.p};
+    CK(ix->h_flags.ensure(nq));
+    const orx::ResultOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                             out_on_dev ? out_counts : ix->h_counts.p, ix->h_flags.p};
     CK(ix->fb_dist.ensure(std::max<size_t>(m, 1)));
     // exact by construction: every eligible row is rescored canonically and the k best are selected
     auto list_query = [&](int j) {
@@ -608,7 +822,6 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
         // bit is clear (HBM traffic = eligible rows only); same candidate proof as orx_search, the rare
         // unproven query is re-answered by the exact list path.
         const uint32_t n_rows = (uint32_t)ix->n_live;
-        CK(ix->h_flags.ensure(nq));
         const int grid = orx::scan_gemv_grid(ix->device, n_rows);
         const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
         ix->scan_ev_used = 0;
@@ -622,8 +835,7 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
             if (e0 && e1) CK(cudaEventRecord(e1, st));
             // n_rows argument = the eligible count: "every eligible row is a candidate" when it fits the list
             orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)s0 * ORX_DIM, ix->prep.p + s0,
-                                 ix->partial.p, grid, slots, mq, k, m, eps, out.ids + (size_t)s0 * k,
-                                 out.dist + (size_t)s0 * k, out.counts + s0, ix->h_flags.p + s0, st);
+                                 ix->partial.p, grid, slots, mq, k, m, eps, out, s0, orx::PublishArgs{}, orx::DoneArgs{}, st);
             ix->stats.kernel_launches += 2;
         }
         CK(cudaStreamSynchronize(st));
@@ -667,19 +879,73 @@ SlotLayout slot_layout(int nq, int k) {
     L.bytes = (L.flags_off + (size_t)nq * sizeof(int) + 15) & ~(size_t)15;
     return L;
 }
-int sharded_round(orx_index *ix, Exchange *x, int nq, int k, const SearchOut &final_out, const SlotLayout &L,
-                  uint32_t seq) {
+// merge what every rank published under `seq` into the caller's result arrays; the last merge CTA writes `token`
+int launch_shard_merge(orx_index *ix, Exchange *x, int nq, int k, const orx::ResultOut &final_out, const SlotLayout &L,
+                       uint32_t seq, uint32_t token) {
     const int set = seq & 1;
-    char *my_slot = x->base + (size_t)set * x->set_bytes + (size_t)x->rank * x->slot_bytes;
-    orx::launch_publish(my_slot, x->d_peer_slot[set], x->d_peer_flag[set], x->world, L.bytes, seq, ix->stream);
     const uint32_t *arrival = reinterpret_cast<const uint32_t *>(x->base + x->flags_off + (size_t)set * x->world * XFLAG_STRIDE);
     orx::launch_merge_wait(x->world, x->rank, nq, k, x->base + (size_t)set * x->set_bytes, x->slot_bytes, L.dist_off,
                            L.counts_off, L.flags_off, arrival, (int)(XFLAG_STRIDE / 4), seq, final_out.ids,
                            final_out.dist, final_out.counts, ix->h_flags.p, ix->h_myflags.p, ix->h_redo.p,
+                           ix->h_done.p + 1, orx::DoneArgs{ix->d_counters.p + 1, (unsigned int)nq, ix->h_done.p, token},
                            ix->stream);
-    ix->stats.kernel_launches += 2;
+    ix->stats.kernel_launches += 1;
     CK(cudaGetLastError());
     return ORX_OK;
+}
+// stand-alone push of the block that sits in my local slot of set (seq & 1) (paths that do not end in finalize)
+int launch_shard_publish(orx_index *ix, Exchange *x, const SlotLayout &L, uint32_t seq) {
+    const int set = seq & 1;
+    char *my_slot = x->base + (size_t)set * x->set_bytes + (size_t)x->rank * x->slot_bytes;
+    orx::launch_publish(my_slot, x->d_peer_slot[set], x->d_peer_flag[set], x->n_targets, L.bytes, seq, ix->stream);
+    ix->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
+// Round 1 of a row-sharded search on ONE shard, launches only (no wait): stage the batch, scan, finalize pushes the
+// shard's block into its targets' gather buffers under `seq`.  On failure the shard still publishes a block whose flags
+// carry bit 3, so that whoever merges fails fast instead of waiting for it.
+int shard_round1(orx_index *ix, Exchange *x, const float *queries, bool src_pinned, int nq, int k, const SlotLayout &L,
+                 uint32_t seq, const float **q_src, int *path) {
+    cudaStream_t st = ix->stream;
+    ix->scan_ev_used = 0;
+    const int set = seq & 1;
+    int rc = ensure_signalling(ix);
+    if (rc == ORX_OK) rc = stage_queries(ix, queries, nq, q_src, src_pinned);
+    if (rc == ORX_OK) {
+        if (ix->n_live == 0) {
+            // an empty shard contributes nothing (its peers may still hold rows); flags carry the query check
+            CK(ix->fb_dist.ensure((L.bytes + 7) / 8));          // scratch block: the shard may own no local slot
+            char *blk = reinterpret_cast<char *>(ix->fb_dist.p);
+            cudaMemsetAsync(blk, 0, L.bytes, st);
+            orx::launch_flags_from_prep(ix->prep.p, nq, reinterpret_cast<int *>(blk + L.flags_off), st);
+            orx::launch_publish(blk, x->d_peer_slot[set], x->d_peer_flag[set], x->n_targets, L.bytes, seq, st);
+            ix->stats.kernel_launches += 2;
+            if (cudaGetLastError() != cudaSuccess) rc = fail(ORX_ERR_CUDA, "publishing an empty shard's block failed");
+        } else {
+            SearchCtx ctx{};
+            ctx.pub = orx::PublishArgs{reinterpret_cast<char *const *>(x->d_peer_slot[set]), x->d_peer_flag[set],
+                                       x->n_targets, seq, L.dist_off, L.counts_off, L.flags_off};
+            ctx.done = orx::DoneArgs{ix->d_counters.p, (unsigned int)nq, nullptr, 0u};
+            rc = scan_pass(ix, *q_src, nq, k, ctx, path);
+        }
+    }
+    if (rc != ORX_OK) {
+        const std::string why = g_err;
+        cudaStreamSynchronize(st);
+        if (ix->d_counters.p) cudaMemsetAsync(ix->d_counters.p, 0, 2 * sizeof(unsigned int), st);
+        if (ix->fb_dist.ensure((L.bytes + 7) / 8) == cudaSuccess) {
+            char *blk = reinterpret_cast<char *>(ix->fb_dist.p);
+            cudaMemsetAsync(blk, 0, L.bytes, st);
+            orx::launch_fill_flags(reinterpret_cast<int *>(blk + L.flags_off), nq, 8, st);
+            orx::launch_publish(blk, x->d_peer_slot[set], x->d_peer_flag[set], x->n_targets, L.bytes, seq, st);
+        }
+        cudaStreamSynchronize(st);
+        cudaGetLastError();
+        g_err = why;
+    }
+    return rc;
 }
 
 int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int nq, int k, orx_id *out_ids,
@@ -690,7 +956,6 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
         return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
     cudaStream_t st = ix->stream;
     const size_t nk = (size_t)nq * k;
-    ix->scan_ev_used = 0;
     const SlotLayout L = slot_layout(nq, k);
     if (L.bytes > x->slot_bytes) return fail(ORX_ERR_INVALID, "sharded search limited to %d queries per call", XQ_MAX);
 
@@ -702,56 +967,65 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
         CK(ix->h_dist.ensure(nk));
         CK(ix->h_counts.ensure(nq));
     }
-    SearchOut final_out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                        out_on_dev ? out_counts : ix->h_counts.p};
+    int rc = ensure_signalling(ix);
+    if (rc != ORX_OK) return rc;
+    const orx::ResultOut final_out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
+                                   out_on_dev ? out_counts : ix->h_counts.p, ix->h_flags.p};
     *ix->h_redo.p = 0;
+    ix->h_done.p[1] = 0;
 
+    // ---- round 1: scan, finalize pushes my block into every rank's gather buffer, merge what arrives
+    const uint32_t seq = ++x->seq;
+    char *slot = x->base + (size_t)(seq & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;      // my block, local copy
     const float *q_src = nullptr;
-    int rc = stage_queries(ix, queries, nq, &q_src);
-    if (rc != ORX_OK) return rc;
-
-    // ---- round 1: scan + finalize into my slot, publish to all peers, merge what arrives
-    uint32_t seq = ++x->seq;
-    char *slot = x->base + (size_t)(seq & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;
-    SearchOut mine{reinterpret_cast<orx_id *>(slot), reinterpret_cast<double *>(slot + L.dist_off),
-                   reinterpret_cast<int *>(slot + L.counts_off)};
-    int *slot_flags = reinterpret_cast<int *>(slot + L.flags_off);
     int path = 1;
-    if (ix->n_live == 0) {
-        // an empty shard contributes nothing (its peers may still hold rows); flags carry the query check
-        CK(cudaMemsetAsync(slot, 0, L.bytes, st));
-        orx::launch_flags_from_prep(ix->prep.p, nq, slot_flags, st);
-        ix->stats.kernel_launches += 1;
-    } else {
-        rc = scan_pass(ix, q_src, nq, k, mine, slot_flags, &path);
-        if (rc != ORX_OK) return rc;
-    }
-    rc = sharded_round(ix, x, nq, k, final_out, L, seq);
+    rc = shard_round1(ix, x, queries, false, nq, k, L, seq, &q_src, &path);
     if (rc != ORX_OK) return rc;
-    CK(cudaStreamSynchronize(st));
+    uint32_t token = next_token(ix);
+    rc = launch_shard_merge(ix, x, nq, k, final_out, L, seq, token);
+    if (rc != ORX_OK) return rc;
+    rc = wait_done(ix, token);
+    if (rc != ORX_OK) return rc;
+    if (ix->h_done.p[1]) return fail(ORX_ERR_CUDA, "sharded search: a peer rank did not publish its candidates within 10 s");
 
-    for (int j = 0; j < nq; ++j)
+    for (int j = 0; j < nq; ++j) {
+        if (ix->h_flags.p[j] & 8) return fail(ORX_ERR_CUDA, "sharded search: a peer rank failed (query %d)", j);
         if (ix->h_flags.p[j] & 2)
             return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+    }
     if (*ix->h_redo.p) {
         // ---- round 2 (every rank sees the same redo word): ranks with unproven queries re-answer them
         //      exactly, everybody republishes and merges again under the next sequence number.
         const uint32_t seq2 = ++x->seq;
         char *slot2 = x->base + (size_t)(seq2 & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;
         CK(cudaMemcpyAsync(slot2, slot, L.bytes, cudaMemcpyDeviceToDevice, st));
-        SearchOut mine2{reinterpret_cast<orx_id *>(slot2), reinterpret_cast<double *>(slot2 + L.dist_off),
-                        reinterpret_cast<int *>(slot2 + L.counts_off)};
-        int *flags2 = reinterpret_cast<int *>(slot2 + L.flags_off);
+        const orx::ResultOut mine2{reinterpret_cast<orx_id *>(slot2), reinterpret_cast<double *>(slot2 + L.dist_off),
+                                   reinterpret_cast<int *>(slot2 + L.counts_off), reinterpret_cast<int *>(slot2 + L.flags_off)};
         bool mine_unproven = false;
         for (int j = 0; j < nq; ++j) mine_unproven |= (ix->h_myflags.p[j] & 1) != 0;
-        if (mine_unproven && ix->n_live > 0) {
-            rc = resolve_unproven(ix, q_src, nq, k, mine2, flags2, ix->h_myflags.p, path, /*host_readable=*/false);
-            if (rc != ORX_OK) return rc;
+        rc = ORX_OK;
+        if (mine_unproven && ix->n_live > 0)
+            rc = resolve_unproven(ix, q_src, nq, k, mine2, ix->h_myflags.p, path, /*host_readable=*/false);
+        if (rc != ORX_OK) {
+            const std::string why = g_err;
+            orx::launch_fill_flags(mine2.flags, nq, 8, st);
+            launch_shard_publish(ix, x, L, seq2);
+            cudaStreamSynchronize(st);
+            cudaGetLastError();
+            g_err = why;
+            return rc;
         }
         *ix->h_redo.p = 0;
-        rc = sharded_round(ix, x, nq, k, final_out, L, seq2);
+        rc = launch_shard_publish(ix, x, L, seq2);
         if (rc != ORX_OK) return rc;
-        CK(cudaStreamSynchronize(st));
+        token = next_token(ix);
+        rc = launch_shard_merge(ix, x, nq, k, final_out, L, seq2, token);
+        if (rc != ORX_OK) return rc;
+        rc = wait_done(ix, token);
+        if (rc != ORX_OK) return rc;
+        if (ix->h_done.p[1]) return fail(ORX_ERR_CUDA, "sharded search: a peer rank did not publish its candidates within 10 s");
+        for (int j = 0; j < nq; ++j)
+            if (ix->h_flags.p[j] & 8) return fail(ORX_ERR_CUDA, "sharded search: a peer rank failed (query %d)", j);
         if (*ix->h_redo.p) return fail(ORX_ERR_CUDA, "sharded search: a rank could not prove its candidates");
     }
     if (!out_on_dev) {
@@ -767,6 +1041,8 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
     ix->stats.queries += nq;
     return ORX_OK;
 }
+
+#include "group.inl"
 
 }  // namespace
 
@@ -792,11 +1068,13 @@ int set_error(int code, const char *fmt, ...) {
     return code;
 }
 cudaStream_t index_stream(const orx_index *ix) {
+    if (ix->group) ix = ix->group->shards[0];          // a multi-GPU index stages on its first device
     std::lock_guard<std::mutex> lk(ix->mu);
     return ix->stream;
 }
 int index_device(const orx_index *ix) { return ix->device; }
 void index_count_launches(orx_index *ix, uint64_t n) {
+    if (ix->group) ix = ix->group->shards[0];
     std::lock_guard<std::mutex> lk(ix->mu);
     ix->stats.kernel_launches += n;
 }
@@ -846,8 +1124,26 @@ int orx_create(orx_index **out, int dim, int dtype, uint64_t capacity_rows, int 
     return ORX_OK;
 }
 
+int orx_create_multi(orx_index **out, int dim, int dtype, uint64_t capacity_rows, const int *devices, int n_devices) {
+    if (!out) return fail(ORX_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "expected %d dimensions, not %d", ORX_DIM, dim);
+    if (dtype != ORX_DTYPE_F32 && dtype != ORX_DTYPE_BF16) return fail(ORX_ERR_INVALID, "unknown dtype %d", dtype);
+    if (!devices || n_devices < 1 || n_devices > 64) return fail(ORX_ERR_INVALID, "n_devices must be in [1, 64]");
+    return group_create(out, dtype, capacity_rows, devices, n_devices);
+}
+
+int orx_shard_count(const orx_index *ix) {
+    if (!ix) return 0;
+    return ix->group ? (int)ix->group->shards.size() : 1;
+}
+
 void orx_destroy(orx_index *ix) {
     if (!ix) return;
+    if (ix->group) {
+        group_destroy(ix);
+        return;
+    }
     DeviceGuard g(ix->device);
     cudaDeviceSynchronize();
     if (ix->umma) orx::umma_plan_destroy(ix->umma);
@@ -876,12 +1172,15 @@ void orx_destroy(orx_index *ix) {
     }
     ix->h_myflags.release();
     ix->h_redo.release();
+    ix->h_done.release();
+    ix->d_counters.release();
     cudaGetLastError();
     delete ix;
 }
 
 int orx_set_stream(orx_index *ix, void *cuda_stream) {
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (ix->group) return fail(ORX_ERR_INVALID, "a multi-GPU index runs on its own per-device streams");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStreamSynchronize(ix->stream);
@@ -891,11 +1190,17 @@ int orx_set_stream(orx_index *ix, void *cuda_stream) {
 
 uint64_t orx_size(const orx_index *ix) {
     if (!ix) return 0;
+    if (ix->group) return group_size(ix->group);
     std::lock_guard<std::mutex> lk(ix->mu);
     return ix->n_live;
 }
 uint64_t orx_capacity(const orx_index *ix) {
     if (!ix) return 0;
+    if (ix->group) {
+        uint64_t c = 0;
+        for (orx_index *s : ix->group->shards) c += orx_capacity(s);
+        return c;
+    }
     std::lock_guard<std::mutex> lk(ix->mu);
     return ix->capacity;
 }
@@ -903,6 +1208,7 @@ int orx_dtype(const orx_index *ix) { return ix ? ix->dtype : -1; }
 
 int orx_get_stats(const orx_index *ix, orx_stats *out) {
     if (!ix || !out) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return group_stats(ix->group, out);
     std::lock_guard<std::mutex> lk(ix->mu);
     *out = ix->stats;
     return ORX_OK;
@@ -910,6 +1216,7 @@ int orx_get_stats(const orx_index *ix, orx_stats *out) {
 
 int orx_contains(const orx_index *ix, orx_id id) {
     if (!ix) return 0;
+    if (ix->group) return orx_contains(ix->group->shards[shard_of_id(id, (uint32_t)ix->group->shards.size())], id);
     std::lock_guard<std::mutex> lk(ix->mu);
     return ix->map.find(id) != ix->map.end() ? 1 : 0;
 }
@@ -920,92 +1227,10 @@ int orx_upsert(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t n, 
     if (n == 0) return ORX_OK;
     if (!ids || !vecs) return fail(ORX_ERR_INVALID, "null ids/vecs");
     if (is_device_ptr(ids)) return fail(ORX_ERR_INVALID, "ids must be a host pointer");
+    if (ix->group) return group_upsert(ix->group, ids, vecs, n);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
-    cudaStream_t st = ix->stream;
-    const bool on_dev = is_device_ptr(vecs);
-    const uint64_t chunk = std::min<uint64_t>(n, STAGE_ROWS);
-
-    CK(ix->d_flag.ensure(1));
-    CK(ix->h_flag.ensure(1));
-    if (!on_dev) CK(ix->stage.ensure(chunk * ORX_DIM));
-
-    // ---- phase 1: pgvector's element check over the WHOLE batch before anything is written
-    CK(cudaMemsetAsync(ix->d_flag.p, 0, sizeof(int), st));
-    for (uint64_t s = 0; s < n; s += chunk) {
-        const uint64_t m = std::min(chunk, n - s);
-        const float *src = vecs + s * ORX_DIM;
-        if (!on_dev) {
-            CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
-            src = ix->stage.p;
-        }
-        orx::launch_validate_rows(src, m, ix->d_flag.p, st);
-        ix->stats.kernel_launches += 1;
-    }
-    CK(cudaMemcpyAsync(ix->h_flag.p, ix->d_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    CK(cudaGetLastError());
-    if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
-
-    // ---- phase 2: plan destinations (existing id -> its row, new id -> append; last duplicate wins)
-    uint64_t n_new = 0;
-    {
-        std::unordered_map<orx_id, int, IdHash, IdEq> seen;
-        if (n > 1) seen.reserve(n);
-        for (uint64_t i = 0; i < n; ++i)
-            if (ix->map.find(ids[i]) == ix->map.end() && seen.emplace(ids[i], 1).second) ++n_new;
-    }
-    int rc = grow_table(ix, ix->n_live + n_new);
-    if (rc != ORX_OK) return rc;
-    if (n_new) ix->generation += 1;
-
-    CK(ix->d_src_idx.ensure(chunk));
-    CK(ix->d_dst_row.ensure(chunk));
-    CK(ix->d_ids.ensure(chunk));
-    CK(ix->h_u32a.ensure(chunk));
-    CK(ix->h_u32b.ensure(chunk));
-    const bool single = (n <= chunk);      // staged data of phase 1 is still resident
-    for (uint64_t s = 0; s < n; s += chunk) {
-        const uint64_t m = std::min(chunk, n - s);
-        // plan this chunk; an id repeated inside the chunk keeps the later source row
-        std::unordered_map<uint32_t, uint32_t> slot_of_row;   // dst row -> plan slot
-        uint32_t np = 0;
-        for (uint64_t i = 0; i < m; ++i) {
-            const orx_id id = ids[s + i];
-            uint32_t row;
-            auto it = ix->map.find(id);
-            if (it != ix->map.end()) row = it->second;
-            else {
-                row = (uint32_t)ix->n_live++;
-                ix->map.emplace(id, row);
-                if (ix->host_row_ids.size() <= row) ix->host_row_ids.resize((size_t)row + 1);
-                ix->host_row_ids[row] = id;
-            }
-            auto ps = slot_of_row.find(row);
-            if (ps != slot_of_row.end()) ix->h_u32a.p[ps->second] = (uint32_t)i;
-            else {
-                slot_of_row.emplace(row, np);
-                ix->h_u32a.p[np] = (uint32_t)i;
-                ix->h_u32b.p[np] = row;
-                ++np;
-            }
-        }
-        const float *src = vecs + s * ORX_DIM;
-        if (!on_dev) {
-            if (!single)
-                CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
-            src = ix->stage.p;
-        }
-        CK(cudaMemcpyAsync(ix->d_src_idx.p, ix->h_u32a.p, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ix->d_dst_row.p, ix->h_u32b.p, np * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(ix->d_ids.p, ids + s, m * sizeof(orx_id), cudaMemcpyHostToDevice, st));
-        orx::launch_commit_rows(ix->dtype, src, ix->d_src_idx.p, ix->d_dst_row.p, ix->d_ids.p, np, ix->table,
-                                ix->scale, ix->n2, ix->row_ids, st);
-        ix->stats.kernel_launches += 1;
-        CK(cudaStreamSynchronize(st));     // h_u32a/b and the caller's buffers are reused next chunk
-    }
-    CK(cudaGetLastError());
-    return ORX_OK;
+    return upsert_locked(ix, ids, vecs, n, /*validate=*/true);
 }
 
 int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed) {
@@ -1013,6 +1238,7 @@ int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
     if (n == 0) return ORX_OK;
     if (!ids) return fail(ORX_ERR_INVALID, "null ids");
+    if (ix->group) return group_delete(ix->group, ids, n, n_removed);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
@@ -1075,6 +1301,7 @@ int orx_search(orx_index *ix, const float *queries, int nq, int dim, int k, orx_
     if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
     if (nq == 0) return ORX_OK;
     if (!queries || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return group_search(ix->group, queries, nq, k, out_ids, out_dist, out_counts);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     return search_locked(ix, queries, nq, k, out_ids, out_dist, out_counts);
@@ -1086,6 +1313,7 @@ int orx_search_filtered(orx_index *ix, const float *queries, int nq, int dim, in
     if (rc != ORX_OK || nq == 0) return rc;
     if (n_allow && !allow_ids) return fail(ORX_ERR_INVALID, "null argument");
     if (is_device_ptr(allow_ids)) return fail(ORX_ERR_INVALID, "allow_ids must be a host pointer");
+    if (ix->group) return group_search_filtered(ix->group, queries, nq, k, allow_ids, n_allow, out_ids, out_dist, out_counts);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     std::vector<uint32_t> rows;
@@ -1101,6 +1329,7 @@ int orx_filter_create(orx_index *ix, const orx_id *allow_ids, uint64_t n_allow, 
     if (!out) return fail(ORX_ERR_INVALID, "out is null");
     *out = nullptr;
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (ix->group) return fail(ORX_ERR_INVALID, "filter handles are per GPU: use orx_search_filtered on a multi-GPU index");
     if (n_allow && !allow_ids) return fail(ORX_ERR_INVALID, "null argument");
     if (is_device_ptr(allow_ids)) return fail(ORX_ERR_INVALID, "allow_ids must be a host pointer");
     orx_filter *f = new orx_filter();
@@ -1149,6 +1378,7 @@ int orx_merge_topk(orx_index *ix, int n_lists, int nq, int k, const orx_id *ids,
         return fail(ORX_ERR_INVALID, "bad merge shape (n_lists=%d, nq=%d, k=%d)", n_lists, nq, k);
     if (nq == 0) return ORX_OK;
     if (!ids || !dist || !counts || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) ix = ix->group->shards[0];
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
@@ -1198,6 +1428,7 @@ int orx_merge_topk_strided(orx_index *ix, int n_lists, int nq, int k, const orx_
         return fail(ORX_ERR_INVALID, "bad merge shape (n_lists=%d, nq=%d, k=%d)", n_lists, nq, k);
     if (nq == 0) return ORX_OK;
     if (!ids0 || !dist0 || !counts0 || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) ix = ix->group->shards[0];
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     orx::launch_merge_topk(n_lists, nq, k, ids0, dist0, counts0, (size_t)list_stride_bytes, out_ids, out_dist,
@@ -1211,6 +1442,7 @@ int orx_export_rows(orx_index *ix, uint64_t row_start, uint64_t n, orx_id *ids_o
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
     if (n == 0) return ORX_OK;
     if (!ids_out || !rows_out) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return group_export_rows(ix->group, row_start, n, ids_out, rows_out);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (row_start + n > ix->n_live) return fail(ORX_ERR_INVALID, "rows [%llu, %llu) exceed the %llu live rows",
@@ -1228,6 +1460,7 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
     if (n == 0) return ORX_OK;
     if (!ids || !rows_raw) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return group_import_rows(ix->group, ids, rows_raw, n);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;
@@ -1270,12 +1503,14 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
 int orx_shard_export(orx_index *ix, int world, int rank, void *handle_out) {
     if (!ix || !handle_out) return fail(ORX_ERR_INVALID, "null argument");
     if (world < 1 || world > 64 || rank < 0 || rank >= world) return fail(ORX_ERR_INVALID, "bad world/rank %d/%d", rank, world);
+    if (ix->group) return fail(ORX_ERR_INVALID, "a multi-GPU index is not a rank of a process group");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (ix->xchg) return fail(ORX_ERR_INVALID, "shard exchange already initialised");
     Exchange *x = new Exchange();
     x->world = world;
     x->rank = rank;
+    x->n_targets = world;
     x->slot_bytes = slot_layout(XQ_MAX, 32).bytes;          // nq * k <= XQ_MAX * 32 per exchange round
     x->set_bytes = x->slot_bytes * world;
     x->flags_off = 2 * x->set_bytes;
@@ -1298,6 +1533,7 @@ int orx_shard_export(orx_index *ix, int world, int rank, void *handle_out) {
 
 int orx_shard_connect(orx_index *ix, const void *handles, int n_handles) {
     if (!ix || !handles) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return fail(ORX_ERR_INVALID, "a multi-GPU index is not a rank of a process group");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     Exchange *x = ix->xchg;
@@ -1346,6 +1582,7 @@ int orx_search_sharded(orx_index *ix, const float *queries, int nq, int dim, int
     if (nq < 0) return fail(ORX_ERR_INVALID, "nq must be >= 0");
     if (nq == 0) return ORX_OK;
     if (!queries || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return fail(ORX_ERR_INVALID, "a multi-GPU index is not a rank of a process group: use orx_search");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     if (!ix->xchg || !ix->xchg->connected) return fail(ORX_ERR_INVALID, "shard exchange not connected (orx_shard_export / orx_shard_connect)");
@@ -1366,6 +1603,7 @@ int orx_fetch(orx_index *ix, const orx_id *ids, uint64_t n, float *out_vecs, int
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
     if (n == 0) return ORX_OK;
     if (!ids || !out_vecs || !out_found) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return group_fetch(ix->group, ids, n, out_vecs, out_found);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
     cudaStream_t st = ix->stream;

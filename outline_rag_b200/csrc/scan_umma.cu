@@ -724,8 +724,8 @@ static cudaError_t ensure_buf(T *&ptr, size_t &have, size_t want) {
 
 int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, const double *n2,
                 const orx_id *row_ids, uint32_t n_rows, const float *q_dev, const float *qhat,
-                const __nv_bfloat16 *qhat16, const QueryPrep *prep, int nq, int k, orx_id *out_ids,
-                double *out_dist, int *out_counts, int *out_flags, cudaStream_t st, uint64_t *launch_counter,
+                const __nv_bfloat16 *qhat16, const QueryPrep *prep, int nq, int k, const ResultOut &out,
+                const PublishArgs &pub, const DoneArgs &done, cudaStream_t st, uint64_t *launch_counter,
                 cudaEvent_t ev_begin, cudaEvent_t ev_end) {
     const bool tf32 = dtype == ORX_DTYPE_F32;
     const double eps = tf32 ? EPS_UMMA_TF32 : EPS_UMMA_BF16;
@@ -781,10 +781,9 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
         }
         if (ev_end && q0 + MAX_Q >= nq) cudaEventRecord(ev_end, st);
         launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, 2, m,
-                        k, n_rows, eps, out_ids + (size_t)q0 * k, out_dist + (size_t)q0 * k, out_counts + q0,
-                        out_flags + q0, st, p->floor);
+                        k, n_rows, eps, out, q0, pub, done, st, p->floor);
 #ifdef ORX_DEBUG_VARIANTS
-        if (p->dbg) launch_flags_from_prep(prep + q0, m, out_flags + q0, st);   // timing experiments: no fallbacks
+        if (p->dbg && out.flags) launch_flags_from_prep(prep + q0, m, out.flags + q0, st);   // timing experiments: no fallbacks
 #endif
         *launch_counter += 2;
         e = cudaGetLastError();

@@ -18,8 +18,8 @@ const char *umma_last_error();
 // Coarse tensor-core scan + finalize for nq queries; writes results and per-query proof flags.
 int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, const double *n2,
                 const orx_id *row_ids, uint32_t n_rows, const float *q_dev, const float *qhat,
-                const __nv_bfloat16 *qhat16, const QueryPrep *prep, int nq, int k, orx_id *out_ids,
-                double *out_dist, int *out_counts, int *out_flags, cudaStream_t st,
+                const __nv_bfloat16 *qhat16, const QueryPrep *prep, int nq, int k, const ResultOut &out,
+                const PublishArgs &pub, const DoneArgs &done, cudaStream_t st,
                 uint64_t *launch_counter, cudaEvent_t ev_begin, cudaEvent_t ev_end);
 
 }  // namespace orx

@@ -45,7 +45,10 @@ __global__ void __launch_bounds__(256)
 commit_rows_kernel(const float *__restrict__ src, const uint32_t *__restrict__ src_idx,
                    const uint32_t *__restrict__ dst_row, const orx_id *__restrict__ ids, uint32_t n,
                    T *__restrict__ table, float *__restrict__ scale, double *__restrict__ n2_out,
-                   orx_id *__restrict__ row_ids) {
+                   orx_id *__restrict__ row_ids, const int *__restrict__ abort_flag) {
+    // the batch's element check (validate_rows, earlier on this stream) found a NaN / Inf: nothing is written --
+    // the whole batch is rejected and the table stays as it was, without a host round trip in between
+    if (abort_flag != nullptr && *abort_flag != 0) return;
     const int lane = threadIdx.x & 31;
     const uint32_t gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const uint32_t n_gw = gridDim.x * (blockDim.x >> 5);
@@ -86,16 +89,16 @@ commit_rows_kernel(const float *__restrict__ src, const uint32_t *__restrict__ s
 
 void launch_commit_rows(int dtype, const float *src, const uint32_t *src_idx, const uint32_t *dst_row,
                         const orx_id *ids, uint32_t n, void *table, float *scale, double *n2,
-                        orx_id *row_ids, cudaStream_t st) {
+                        orx_id *row_ids, const int *abort_flag, cudaStream_t st) {
     if (n == 0) return;
     uint32_t blocks = (n + 7) / 8;
     blocks = cap_grid(blocks, 8);
     if (dtype == ORX_DTYPE_F32)
         commit_rows_kernel<float><<<blocks, 256, 0, st>>>(src, src_idx, dst_row, ids, n,
-                                                          static_cast<float *>(table), scale, n2, row_ids);
+                                                          static_cast<float *>(table), scale, n2, row_ids, abort_flag);
     else
         commit_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(
-            src, src_idx, dst_row, ids, n, static_cast<__nv_bfloat16 *>(table), scale, n2, row_ids);
+            src, src_idx, dst_row, ids, n, static_cast<__nv_bfloat16 *>(table), scale, n2, row_ids, abort_flag);
 }
 
 // Bulk load (snapshot restore / cold start): the rows were copied VERBATIM (table dtype) to the

@@ -182,12 +182,26 @@ class Index:
     ``dtype``: ``"fp32"`` keeps rows verbatim (bit-exact ids vs the oracle), ``"bf16"`` stores
     RNE-bf16 of the normalised row (half the HBM traffic; recall@k is reported)."""
 
-    def __init__(self, dtype="fp32", capacity: int = 0, device: int | None = None, dim: int = ORX_DIM):
-        if device is None:
-            device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+    def __init__(self, dtype="fp32", capacity: int = 0, device: int | None = None, dim: int = ORX_DIM,
+                 devices: Sequence[int] | None = None):
+        """``devices=[0, 1, ..., 7]``: ONE table row-sharded over those GPUs, driven by this process
+        (`orx_create_multi`; rows placed by ``mix64(id) mod len(devices)``; searches run on all GPUs at once and the
+        k candidates per query meet on ``devices[0]`` over NVLink).  Same methods as a single-GPU index."""
         self._h = C.c_void_p()
-        self.device = int(device)
-        check(lib.orx_create(C.byref(self._h), int(dim), _DTYPES[dtype], int(capacity), self.device))
+        if devices is not None:
+            devs = [int(d) for d in devices]
+            if not devs:
+                raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "devices must not be empty")
+            arr = (C.c_int * len(devs))(*devs)
+            self.device = devs[0]
+            self.devices = devs
+            check(lib.orx_create_multi(C.byref(self._h), int(dim), _DTYPES[dtype], int(capacity), arr, len(devs)))
+        else:
+            if device is None:
+                device = torch.cuda.current_device() if (torch is not None and torch.cuda.is_available()) else 0
+            self.device = int(device)
+            self.devices = [self.device]
+            check(lib.orx_create(C.byref(self._h), int(dim), _DTYPES[dtype], int(capacity), self.device))
         self.dtype = "fp32" if _DTYPES[dtype] == DTYPE_F32 else "bf16"
 
     # -- lifetime
@@ -215,8 +229,15 @@ class Index:
     def capacity(self) -> int:
         return int(lib.orx_capacity(self._h))
 
+    @property
+    def shard_count(self) -> int:
+        return int(lib.orx_shard_count(self._h))
+
     def use_torch_stream(self) -> None:
-        """Launch on torch's current stream so ``torch.cuda.Event`` timing sees the kernels."""
+        """Launch on torch's current stream so ``torch.cuda.Event`` timing sees the kernels (single-GPU index; a
+        multi-GPU index runs on its own per-device streams and every call returns only when its result is there)."""
+        if len(self.devices) > 1 or self.shard_count > 1:
+            return
         check(lib.orx_set_stream(self._h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
     def set_stream(self, cuda_stream: int) -> None:

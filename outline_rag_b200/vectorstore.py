@@ -30,9 +30,20 @@ from ._lib import ORX_DIM, ORX_ERR_DIM, ORX_ERR_NONFINITE, OrxValueError
 from .batcher import QueryBatcher
 from .engine import Filter, Index, ids_to_array, ids_to_uuid_strs
 
-try:  # use the real class when the host application has langchain installed
+# The reference's seam is typed: `rag.vector_store: AsyncPGVectorStore` (a langchain VectorStore), its
+# `.as_retriever(...)` result is handed to the pydantic-validated `ContextualCompressionRetriever(base_retriever=...)`
+# (reference app/rag.py:28-31, :85-99).  So when the host application has langchain-core, GpuVectorStore IS a
+# `langchain_core.vectorstores.VectorStore` and `as_retriever` returns langchain's own `VectorStoreRetriever`
+# (a `BaseRetriever` / Runnable).  Without langchain (this image; tests) the same class stands on `object` and
+# `as_retriever` returns the duck-typed `GpuRetriever`.
+try:
     from langchain_core.documents import Document  # type: ignore
+    from langchain_core.vectorstores import VectorStore as _VectorStoreBase  # type: ignore
+    HAVE_LANGCHAIN = True
 except Exception:
+    HAVE_LANGCHAIN = False
+    _VectorStoreBase = object
+
     @dataclass
     class Document:  # same three fields `rag.py` / `api.py` touch
         page_content: str
@@ -136,7 +147,8 @@ def _canon_uuid(v) -> str:
 
 
 class GpuRetriever:
-    """``VectorStoreRetriever`` stand-in (search_type="similarity")."""
+    """``VectorStoreRetriever`` stand-in (search_type="similarity") for hosts WITHOUT langchain-core; with it,
+    `GpuVectorStore.as_retriever` returns langchain's own ``VectorStoreRetriever``."""
 
     def __init__(self, store: "GpuVectorStore", search_kwargs: Optional[dict] = None):
         self.vectorstore = store
@@ -149,7 +161,7 @@ class GpuRetriever:
         return self.vectorstore.similarity_search(query, **self.search_kwargs)
 
 
-class GpuVectorStore:
+class GpuVectorStore(_VectorStoreBase):
     def __init__(self, index: Index, embedding_service, doc_store=None,
                  metadata_columns: Optional[list[str]] = None, table_name: str = "langchain_pg_embedding",
                  batch_window_ms: Optional[float] = None, max_batch: int = 256):
@@ -165,27 +177,61 @@ class GpuVectorStore:
     @classmethod
     async def create(cls, engine=None, embedding_service=None, table_name: str = "langchain_pg_embedding",
                      metadata_columns: Optional[list[str]] = None, *, dtype: str = "fp32", capacity: int = 0,
-                     device: Optional[int] = None, doc_store=None, batch_window_ms: Optional[float] = None,
-                     max_batch: int = 256, **_: Any) -> "GpuVectorStore":
+                     device: Optional[int] = None, devices: Optional[Sequence[int]] = None, doc_store=None,
+                     batch_window_ms: Optional[float] = None, max_batch: int = 256, **_: Any) -> "GpuVectorStore":
         """Same call shape as ``AsyncPGVectorStore.create`` (reference app/rag.py:69-79).
         ``engine`` (the PGEngine) is accepted and handed to the doc store factory if it is
-        callable; the vector column itself now lives in HBM."""
+        callable; the vector column itself now lives in HBM.  ``devices=[0..7]`` row-shards the table over
+        those GPUs inside this process (`orx_create_multi`): same object, same methods."""
         if embedding_service is None:
             raise ValueError("embedding_service is required")
         if callable(doc_store):
             doc_store = doc_store(engine)
-        index = await asyncio.to_thread(Index, dtype, capacity, device)
+        index = await asyncio.to_thread(lambda: Index(dtype, capacity, device, devices=devices))
         return cls(index, embedding_service, doc_store, metadata_columns, table_name, batch_window_ms, max_batch)
 
     @classmethod
     def create_sync(cls, embedding_service, **kw) -> "GpuVectorStore":
         doc_store = kw.pop("doc_store", None)
-        index = Index(kw.pop("dtype", "fp32"), kw.pop("capacity", 0), kw.pop("device", None))
+        index = Index(kw.pop("dtype", "fp32"), kw.pop("capacity", 0), kw.pop("device", None), devices=kw.pop("devices", None))
         return cls(index, embedding_service, doc_store, kw.pop("metadata_columns", None),
                    kw.pop("table_name", "langchain_pg_embedding"))
 
-    def as_retriever(self, search_kwargs: Optional[dict] = None, **_: Any) -> GpuRetriever:
-        return GpuRetriever(self, search_kwargs)
+    def as_retriever(self, **kwargs: Any):
+        """``vector_store.as_retriever(search_kwargs={"k": TOP_K})`` (reference app/rag.py:85-87).  With
+        langchain-core: the inherited ``VectorStore.as_retriever`` -> a real ``VectorStoreRetriever`` (``BaseRetriever``,
+        accepted by ``ContextualCompressionRetriever(base_retriever=...)``, rag.py:96-99) that calls
+        ``asimilarity_search(query, **search_kwargs)``.  Without it: the duck-typed `GpuRetriever`."""
+        if HAVE_LANGCHAIN:
+            return super().as_retriever(**kwargs)
+        return GpuRetriever(self, kwargs.get("search_kwargs"))
+
+    # -- the rest of langchain's abstract VectorStore surface
+    @property
+    def embeddings(self):
+        return self.embedding_service
+
+    def add_texts(self, texts, metadatas: Optional[Sequence[dict]] = None, *, ids: Optional[Sequence] = None,
+                  **_: Any) -> list[str]:
+        texts = list(texts)
+        if not texts:
+            return []
+        return self.add_embeddings(texts, self.embedding_service.embed_documents(texts), metadatas, ids)
+
+    async def aadd_texts(self, texts, metadatas: Optional[Sequence[dict]] = None, *, ids: Optional[Sequence] = None,
+                         **_: Any) -> list[str]:
+        texts = list(texts)
+        if not texts:
+            return []
+        emb = await self.embedding_service.aembed_documents(texts)
+        return await self.aadd_embeddings(texts, emb, metadatas, ids)
+
+    @classmethod
+    def from_texts(cls, texts, embedding, metadatas: Optional[Sequence[dict]] = None, **kw: Any) -> "GpuVectorStore":
+        ids = kw.pop("ids", None)
+        store = cls.create_sync(embedding, **kw)
+        store.add_texts(texts, metadatas, ids=ids)
+        return store
 
     # ---------------------------------------------------------------- writes
     def add_embeddings(self, texts: Sequence[str], embeddings, metadatas: Optional[Sequence[dict]] = None,
@@ -233,7 +279,7 @@ class GpuVectorStore:
         emb = await self.embedding_service.aembed_documents(texts)
         return await self.aadd_embeddings(texts, emb, metas, ids)
 
-    def add_documents(self, documents: Sequence, ids: Optional[Sequence] = None) -> list[str]:
+    def add_documents(self, documents: Sequence, ids: Optional[Sequence] = None, **_: Any) -> list[str]:
         texts = [d.page_content for d in documents]
         metas = [dict(getattr(d, "metadata", {}) or {}) for d in documents]
         if ids is None:
@@ -291,7 +337,9 @@ class GpuVectorStore:
         rows = self.doc_store.get_many(sids)
         out = []
         for sid, row, d in zip(sids, rows, dist_row[:count]):
-            content, meta = row if row is not None else ("", {})
+            if row is None:      # the chunk left the source of truth after the scan (a delete in flight): the SQL
+                continue         # would not have returned it either
+            content, meta = row
             out.append((Document(page_content=content, metadata=dict(meta), id=sid), float(d)))
         return out
 
@@ -341,4 +389,4 @@ class GpuVectorStore:
         return [d for d, _ in self.similarity_search_with_score_by_vector(emb, k, **kw)]
 
 
-__all__ = ["GpuVectorStore", "GpuRetriever", "MemoryDocStore", "Document", "DEFAULT_METADATA_COLUMNS"]
+__all__ = ["GpuVectorStore", "GpuRetriever", "MemoryDocStore", "Document", "DEFAULT_METADATA_COLUMNS", "HAVE_LANGCHAIN"]
