@@ -87,6 +87,11 @@ int orx_shard_count(const orx_index *idx);      /* 1 for orx_create, n_devices f
  * stream).  Python hands over torch's current stream so torch.cuda.Event sees them. */
 int orx_set_stream(orx_index *idx, void *cuda_stream);
 
+/* Options.  ORX_OPT_SCAN_TIMING (default 1): record a CUDA event pair around every scan launch so that orx_get_stats
+ * can report the scan kernel's own device time (bench.py's roofline); 0 saves the two event records per search. */
+#define ORX_OPT_SCAN_TIMING 1
+int orx_set_option(orx_index *idx, int option, int value);
+
 uint64_t orx_size(const orx_index *idx);       /* live rows */
 uint64_t orx_capacity(const orx_index *idx);
 int orx_dtype(const orx_index *idx);

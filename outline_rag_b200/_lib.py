@@ -22,6 +22,7 @@ CSRC_DIR = os.path.join(_HERE, "csrc")
 
 ORX_DIM = 1024
 ORX_MAX_K = 128
+ORX_OPT_SCAN_TIMING = 1
 ORX_IPC_HANDLE_BYTES = 64
 DTYPE_F32 = 0
 DTYPE_BF16 = 1
@@ -77,6 +78,7 @@ SIGNATURES = {
     "orx_shard_count": (C.c_int, [_vp]),
     "orx_destroy": (None, [_vp]),
     "orx_set_stream": (C.c_int, [_vp, _vp]),
+    "orx_set_option": (C.c_int, [_vp, C.c_int, C.c_int]),
     "orx_size": (C.c_uint64, [_vp]),
     "orx_capacity": (C.c_uint64, [_vp]),
     "orx_dtype": (C.c_int, [_vp]),

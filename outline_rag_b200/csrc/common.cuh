@@ -153,6 +153,14 @@ __device__ __forceinline__ bool sorts_before(double da, uint64_t ahi, uint64_t a
     return alo < blo;
 }
 
+// ---------------------------------------------- programmatic dependent launch (PDL)
+// The kernels of one search chain (prep -> scan -> finalize) are launched with the programmatic-stream-serialization
+// attribute: a dependent grid may be scheduled while its predecessor still runs and parks at pdl_wait() until the
+// predecessor has completed and its writes are visible, so the launch latency of each kernel hides behind the one
+// before it.  Both instructions are no-ops for a kernel launched the plain way.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------ streaming loads
 __device__ __forceinline__ float4 ldg_stream_f4(const float4 *p) {
     float4 r;

@@ -147,12 +147,16 @@ merge_wait_kernel(int world, int rank, int nq, int k, const char *__restrict__ s
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
-            const unsigned int old = atomicAdd(done.counter, 1u);
-            if (old + 1u == done.total) {
-                *done.counter = 0u;
-                __threadfence_system();
-                if (done.done_host != nullptr) *reinterpret_cast<volatile uint32_t *>(done.done_host) = done.token;
+            bool last = done.total == 1u;
+            if (!last) {
+                const unsigned int old = atomicAdd(done.counter, 1u);
+                if (old + 1u == done.total) {
+                    *done.counter = 0u;
+                    __threadfence_system();
+                    last = true;
+                }
             }
+            if (last && done.done_host != nullptr) *reinterpret_cast<volatile uint32_t *>(done.done_host) = done.token;
         }
     }
 }

@@ -20,6 +20,7 @@ prep_queries_kernel(const float *__restrict__ q_all, int nq, float *__restrict__
                     QueryPrep *__restrict__ prep) {
     const int lane = threadIdx.x & 31;
     const int qi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_launch_dependents();            // the scan's CTAs may take their SMs now; they wait for this grid before reading qhat
     if (qi >= nq) return;
     const float *q = q_all + (size_t)qi * ORX_DIM;
     float x[32];
@@ -126,6 +127,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         s_kth = __longlong_as_double(0x7ff8000000000000ll);
         s_valid = 0;
     }
+    pdl_wait();                         // the scan that filled `partial` has completed (no-op for a plain launch)
 
     // 1. the query's top-K candidates by fast score.
     __shared__ uint64_t s_surv[FIN_SURV];
@@ -243,9 +245,10 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     }
     const uint64_t *s_cand = s_keys[0];
 
-    // 2. canonical rescore, one warp per candidate.  Coarse (tcgen05) candidates that are more than the
-    //    margin below the k-th best COARSE score cannot reach the top-k (same argument as the scan's
-    //    running threshold), so they are not rescored; the proof below accounts for them through `cut`.
+    // 2. canonical rescore, one warp per candidate.  A candidate whose fast score is more than 2*eps (+ slack) below
+    //    the k-th best FAST score cannot reach the top-k (|fast - cosine| <= eps for both), so it is not rescored; the
+    //    proof below accounts for the ones left out through `cut`.  With k = 12 of K = 32 candidates that is one
+    //    round of 16 warps instead of two.
     __shared__ unsigned char s_ok[K];
     float *s_q = reinterpret_cast<float *>(s_all);          // the bitonic scratch is free now: stage the query (4 KB)
     const float *q = q_all + (size_t)qi * ORX_DIM;
@@ -253,8 +256,8 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     for (int e = threadIdx.x; e < ORX_DIM; e += FIN_THREADS) s_q[e] = q[e];
     const double n2q = prep[qi].n2q;
     float cut = __int_as_float(0xff800000);               // -inf: nothing is cut
-    if (floor_all != nullptr) {
-        // s_cand is sorted by key, descending: untrusted (ORD_ALWAYS) rows first, then by coarse score;
+    {
+        // s_cand is sorted by key, descending: untrusted (ORD_ALWAYS) rows first, then by fast score;
         // the cut hangs on the k-th best REGULAR candidate
         int n_always = 0;
         for (int c = 0; c < K; ++c) n_always += (key_ord(s_cand[c]) == ORD_ALWAYS);
@@ -266,6 +269,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         return key == 0ull || (key_ord(key) != ORD_ALWAYS && ord_to_float(key_ord(key)) <= cut);
     };
     __syncthreads();
+    // candidates are sorted by fast score, so the ones to rescore are a prefix (plus nothing after the first cut one)
     for (int c = warp; c < K; c += FIN_WARPS) {
         const uint64_t key = s_cand[c];
         // the row this warp takes in the NEXT round: pull its 32 lines towards L2 now (one line per lane)
@@ -358,9 +362,13 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
                     bound += eps;
                     flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
                 }
-            } else if (ord_last == ORD_NAN) flag = 0;  // everything outside is a NaN row
+            } else if (ord_last == ORD_NAN && !((double)cut > -1.0e30)) flag = 0;  // everything outside is a NaN row
             else {
-                const double bound = (double)ord_to_float(ord_last) + eps;
+                // rows outside the list have fast score <= the list's K-th; listed rows that were not rescored have
+                // fast score <= cut
+                double bound = ord_last == ORD_NAN ? -1.0e30 : (double)ord_to_float(ord_last);
+                if ((double)cut > bound) bound = (double)cut;
+                bound += eps;
                 flag = ((1.0 - dk) > bound && dk < 2.0) ? 0 : 1;
             }
         }
@@ -380,10 +388,16 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         __threadfence_system();
         __syncthreads();
         if (t == 0) {
-            const unsigned int old = atomicAdd(done.counter, 1u);
-            if (old + 1u == done.total) {
-                *done.counter = 0u;
-                __threadfence_system();
+            bool last = done.total == 1u;                  // a single-query search has one CTA: nothing to count
+            if (!last) {
+                const unsigned int old = atomicAdd(done.counter, 1u);
+                if (old + 1u == done.total) {
+                    *done.counter = 0u;
+                    __threadfence_system();
+                    last = true;
+                }
+            }
+            if (last) {
                 for (int o = 0; o < pub.n_targets; ++o) *reinterpret_cast<volatile uint32_t *>(pub.flag[o]) = pub.seq;
                 if (done.done_host != nullptr) *reinterpret_cast<volatile uint32_t *>(done.done_host) = done.token;
             }
@@ -398,8 +412,8 @@ static void launch_finalize_t(const void *table, const double *n2, const orx_id 
                               const PublishArgs &pub, const DoneArgs &done, cudaStream_t st, const float *floor) {
     const T *tab = static_cast<const T *>(table);
 #define ORX_FIN(S_)                                                                                          \
-    finalize_kernel<T, S_><<<nq, FIN_THREADS, 0, st>>>(tab, n2, row_ids, q, prep, partial, nparts, k, n_rows, eps, \
-                                                       out, q_base, pub, done, floor, floor == nullptr)
+    launch_pdl(finalize_kernel<T, S_>, dim3(nq), dim3(FIN_THREADS), 0, st, tab, n2, row_ids, q, prep, partial, nparts, k, \
+               n_rows, eps, out, q_base, pub, done, floor, (int)(floor == nullptr))
     switch (slots) {
         case 1: ORX_FIN(1); break;
         case 2: ORX_FIN(2); break;

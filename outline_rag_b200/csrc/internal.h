@@ -119,6 +119,22 @@ void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint
 void launch_decode_pgvector(const uint8_t *raw, const uint64_t *payload_off, uint32_t n, float *out,
                             cudaStream_t st);
 
+// launch `kernel` on `st` with the programmatic-stream-serialization attribute (common.cuh: PDL)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // SM count of the CURRENT device (cached per device): launch geometry is sized from it, never from a literal
 int device_sms();
 template <typename T> inline T cap_grid(T blocks, int ctas_per_sm) {     // persistent-style grids: <= ctas_per_sm x SMs

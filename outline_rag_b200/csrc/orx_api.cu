@@ -187,6 +187,7 @@ struct orx_index {
     PinBuf<uint32_t> h_done;            // [0] completion word the last CTA of a search writes (host polls it), [1] error word
     DevBuf<unsigned int> d_counters;    // [0] finalize CTAs, [1] merge CTAs of the search in flight (0 between searches)
     uint32_t token = 0;                 // last completion token handed out (never 0)
+    bool scan_timing = true;            // ORX_OPT_SCAN_TIMING
     struct Exchange *xchg = nullptr;     // peer-memory exchange of the row-sharded search (orx_shard_*)
     struct Group *group = nullptr;       // non-null: this handle is a multi-GPU group (orx_create_multi); shard fields unused
     // filtered search: eligibility bitmap (one bit per row) for the filtered scan
@@ -414,6 +415,7 @@ int upsert_locked(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t 
 // ---------------------------------------------------------------- search core
 // a fresh event from the per-search pool (pairs: before / after one scan launch)
 cudaEvent_t scan_event(orx_index *ix) {
+    if (!ix->scan_timing) return nullptr;
     if (ix->scan_ev_used == ix->scan_ev.size()) {
         cudaEvent_t e = nullptr;
         if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
@@ -645,9 +647,7 @@ int resolve_unproven(orx_index *ix, const float *q_src, int nq, int k, const orx
 int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
                   int *out_counts) {
     const auto t_begin = std::chrono::steady_clock::now();
-    const bool out_on_dev = is_device_ptr(out_ids);
-    if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
-        return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
+    const bool out_on_dev = is_device_ptr(out_ids);        // (out_dist / out_counts are documented to be of the same kind)
     cudaStream_t st = ix->stream;
     const size_t nk = (size_t)nq * k;
     ix->scan_ev_used = 0;
@@ -1185,6 +1185,18 @@ int orx_set_stream(orx_index *ix, void *cuda_stream) {
     DeviceGuard g(ix->device);
     cudaStreamSynchronize(ix->stream);
     ix->stream = static_cast<cudaStream_t>(cuda_stream);
+    return ORX_OK;
+}
+
+int orx_set_option(orx_index *ix, int option, int value) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (option != ORX_OPT_SCAN_TIMING) return fail(ORX_ERR_INVALID, "unknown option %d", option);
+    if (ix->group) {
+        for (orx_index *s : ix->group->shards) orx_set_option(s, option, value);
+        return ORX_OK;
+    }
+    std::lock_guard<std::mutex> lk(ix->mu);
+    ix->scan_timing = value != 0;
     return ORX_OK;
 }
 

@@ -38,6 +38,8 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
     const float *qhat = qhat_all + (size_t)query * ORX_DIM;
     uint64_t *partial = partial_all + ((size_t)query * gridDim.x + blockIdx.x) * K;
 
+    pdl_launch_dependents();          // finalize may be scheduled as soon as an SM has room; it parks at its own wait
+    pdl_wait();                       // prep_queries (qhat) and the previous reader of `partial` are done
     float4 qv[8];
     load_q_slice<T>(qhat, lane, qv);
 
@@ -199,10 +201,10 @@ static void launch_scan_gemv_t(const void *table, const float *scale, uint32_t n
     dim3 g(grid, nq);
     const T *tab = static_cast<const T *>(table);
     switch (slots) {
-        case 1: scan_gemv_kernel<T, 1><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
-        case 2: scan_gemv_kernel<T, 2><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
-        case 4: scan_gemv_kernel<T, 4><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
-        default: scan_gemv_kernel<T, 5><<<g, SCAN_THREADS, 0, st>>>(tab, scale, n_rows, qhat, partial); break;
+        case 1: launch_pdl(scan_gemv_kernel<T, 1>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, partial); break;
+        case 2: launch_pdl(scan_gemv_kernel<T, 2>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, partial); break;
+        case 4: launch_pdl(scan_gemv_kernel<T, 4>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, partial); break;
+        default: launch_pdl(scan_gemv_kernel<T, 5>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, partial); break;
     }
 }
 

@@ -243,6 +243,9 @@ class Index:
     def set_stream(self, cuda_stream: int) -> None:
         check(lib.orx_set_stream(self._h, C.c_void_p(cuda_stream)))
 
+    def set_option(self, option: int, value: int) -> None:
+        check(lib.orx_set_option(self._h, int(option), int(value)))
+
     def stats(self) -> dict:
         st = OrxStats()
         check(lib.orx_get_stats(self._h, C.byref(st)))
@@ -286,12 +289,13 @@ class Index:
         return out, found.astype(bool)
 
     # -- reads
-    def search(self, queries, k: int = 12):
+    def search(self, queries, k: int = 12, out=None):
         """Exact ``ORDER BY embedding <=> :q LIMIT :k`` for each query row.
 
         Host input (NumPy / CPU tensor) -> NumPy ``(ids uint64 [nq,k,2], dist float64 [nq,k],
         counts int32 [nq])``.  CUDA tensor input -> the same as device tensors (ids int64 bit
-        patterns), no host copies of the results."""
+        patterns), no host copies of the results; ``out`` = (ids, dist, counts) CUDA tensors to write into
+        (a closed loop of searches then allocates nothing)."""
         if _is_cuda_tensor(queries):
             q = queries.contiguous()
             if q.dim() == 1:
@@ -299,9 +303,12 @@ class Index:
             if q.dtype != torch.float32:
                 raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "device queries must be float32")
             nq, dim = q.shape
-            ids = torch.empty((nq, k, 2), dtype=torch.int64, device=q.device)
-            dist = torch.empty((nq, k), dtype=torch.float64, device=q.device)
-            cnt = torch.empty((nq,), dtype=torch.int32, device=q.device)
+            if out is not None:
+                ids, dist, cnt = out
+            else:
+                ids = torch.empty((nq, k, 2), dtype=torch.int64, device=q.device)
+                dist = torch.empty((nq, k), dtype=torch.float64, device=q.device)
+                cnt = torch.empty((nq,), dtype=torch.int32, device=q.device)
             check(lib.orx_search(self._h, C.c_void_p(q.data_ptr()), nq, dim, int(k), C.c_void_p(ids.data_ptr()),
                                  C.c_void_p(dist.data_ptr()), C.c_void_p(cnt.data_ptr())))
             return ids, dist, cnt

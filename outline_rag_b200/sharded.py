@@ -185,6 +185,15 @@ class ShardedIndex:
             self.local.merge_blocks(p["gathered"], self.world, nq, k, p["words"] * 8, p["out_ids"], p["out_dist"],
                                     p["out_cnt"])
             return p["out_ids"], p["out_dist"], p["out_cnt"]
+        if self.world == 1 and isinstance(queries, torch.Tensor) and queries.is_cuda and isinstance(self.local, Index):
+            q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+            key = (q.shape[0], k)
+            out = self._outs.get(key)
+            if out is None:
+                out = self._outs[key] = (torch.empty((q.shape[0], k, 2), dtype=torch.int64, device=q.device),
+                                         torch.empty((q.shape[0], k), dtype=torch.float64, device=q.device),
+                                         torch.empty((q.shape[0],), dtype=torch.int32, device=q.device))
+            return self.local.search(q, k, out=out)
         ids, dist_, cnt = self.local.search(queries, k)
         if self.world == 1:
             return ids, dist_, cnt

@@ -396,11 +396,17 @@ def test_vectorstore_cold_start_from_an_async_copy_stream():
 
     async def run():
         store = await orx.GpuVectorStore.create(None, Emb())
+        # content and metadata live in the doc store (Postgres in production); only the vectors are streamed
+        sids = orx.ids_to_uuid_strs(ids)
+        store.doc_store.put_many(sids, [f"chunk {i}" for i in range(300)], [{"source_id": "d"}] * 300)
         assert await store.aload_pgcopy(chunks(), feed_bytes=100_000) == (300, 0)
         # the text form of the query vector, as the reference sends it
         q = orx.parse_vector_text(W.langchain_text(X[42]))
         hits = await store.asimilarity_search_with_score_by_vector(q, k=3)
-        assert hits[0][0].id == orx.ids_to_uuid_strs(ids[42:43])[0] and hits[0][1] < 1e-12
+        assert hits[0][0].id == sids[42] and hits[0][0].page_content == "chunk 42" and hits[0][1] < 1e-12
+        # a chunk that has left the source of truth is not returned (the SQL would not return it either)
+        store.doc_store.delete_many([sids[42]])
+        assert all(h[0].id != sids[42] for h in await store.asimilarity_search_with_score_by_vector(q, k=3))
         store.index.close()
 
     asyncio.run(run())
