@@ -69,6 +69,8 @@ def parse_args():
     ap.add_argument("--mixed", action="store_true",
                     help="config 5: REFRESH_BATCH_SIZE=50-doc delete+upsert between every 100 single-query searches")
     ap.add_argument("--mixed-rounds", type=int, default=20)
+    ap.add_argument("--no-group-e2e", action="store_true",
+                    help="N > 1: keep e2e on the rank-per-GPU path instead of the one-process multi-GPU index")
     ap.add_argument("--lib", default=None, help="A/B: load this build of liborx.so instead of the in-tree default")
     return ap.parse_args()
 
@@ -343,7 +345,10 @@ class Bench:
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             import datetime
             dist.init_process_group("nccl", device_id=torch.device(f"cuda:{self.local}"),
-                                    timeout=datetime.timedelta(seconds=600))
+                                    timeout=datetime.timedelta(seconds=900))
+            # a CPU-side group: ranks that wait for rank 0's one-process multi-GPU leg must not park a spinning NCCL
+            # kernel on the GPUs that leg is measuring
+            self.cpu_group = dist.new_group(backend="gloo", timeout=datetime.timedelta(seconds=900))
         self.hbm_peak, self.tensor_peak, self.tensor_sustained, self.peak_src = measured_peaks()
 
     def barrier(self):
@@ -386,6 +391,54 @@ class Bench:
         if self.world > 1:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return float(ms.item()), lat
+
+    # -------------------------------------------------------------- e2e at N > 1: ONE process drives all the GPUs
+    def group_e2e(self, rows, dtype, B, steps, warmup, check_queries, check_ids, check_dist):
+        """The call a user of the drop-in makes on a multi-GPU box: `Index(devices=[0..N-1])` (what
+        `GpuVectorStore.create(devices=...)` wraps; `orx_create_multi`) searched with HOST buffers -- the query batch
+        goes host->device on every GPU, the k candidates per query meet on GPU 0 over NVLink peer memory, ids /
+        distances / counts come back device->host, all inside the timed region.  Runs on rank 0 after the ranks have
+        freed their tables; the other ranks wait on a CPU barrier."""
+        import outline_rag_b200 as orx
+        from orx_testkit.synth import Synth, default_centres
+        torch = self.torch
+        out = None
+        if self.rank == 0:
+            devs = list(range(self.world))
+            t0 = time.perf_counter()
+            ix = orx.Index(dtype, rows, devices=devs)
+            build_table(ix.upsert, 0, rows, 0, 1)
+            build_s = time.perf_counter() - t0
+            assert len(ix) == rows
+            n_batches = 8 if B * 8 <= 4096 else 1
+            Qh, _ = Synth(default_centres(rows)).queries(max(B * n_batches, len(check_queries)), rows)
+            Qpin = torch.from_numpy(Qh).pin_memory()
+            host_batches = [Qpin[j * B:(j + 1) * B].numpy() for j in range(n_batches)]
+            for i in range(max(warmup, 3)):
+                ix.search(host_batches[i % n_batches], K)
+            lat = np.empty(steps)
+            t_all = time.perf_counter()
+            for i in range(steps):
+                t = time.perf_counter()
+                ix.search(host_batches[i % n_batches], K)
+                lat[i] = time.perf_counter() - t
+            wall = time.perf_counter() - t_all
+            same = True
+            for j in range(len(check_queries)):
+                g = ix.search(check_queries[j:j + 1], K)
+                same &= bool(np.array_equal(g[0][0], np.asarray(check_ids[j], np.uint64).reshape(-1, 2)))
+                same &= bool(np.array_equal(g[1][0].view(np.uint64), np.asarray(check_dist[j], np.float64).view(np.uint64)))
+            st = ix.stats()
+            ix.close()
+            out = {"value": B * steps / wall, "unit": UNIT, "h2d_bytes_per_step": B * DIM * 4 * self.world,
+                   "d2h_bytes_per_step": B * K * (16 + 8) + B * 4, "p50_ms": float(np.median(lat) * 1e3),
+                   "p99_ms": float(np.percentile(lat, 99) * 1e3), "steps": steps,
+                   "api": f"Index(devices={devs}).search on NumPy (host) buffers: one process, orx_create_multi, "
+                          f"finalize -> peer stores into GPU 0 -> merge_wait -> mapped host memory",
+                   "same_ids_and_distance_bits_as_the_rank_per_gpu_path": same, "table_build_s": round(build_s, 2),
+                   "kernel_launches_total": int(st["kernel_launches"])}
+        self.dist.barrier(group=self.cpu_group)
+        return out
 
     # -------------------------------------------------------------- full-scan parity
     def full_scan_verify(self, sh, Qv, k, engine_ids, engine_dist, dtype):
@@ -502,6 +555,7 @@ class Bench:
                 e_ids += list(o[0])
                 e_dist += list(o[1])
             verify = self.full_scan_verify(sh, Qh[:nv], K, e_ids[:nv], e_dist[:nv], dtype)
+            self.last_check = (Qh[:nv].copy(), e_ids[:nv], e_dist[:nv])
         if self.rank != 0:
             return None
 
@@ -563,6 +617,7 @@ def run_ours(a):
 
     sh, owned, build_s = bn.build(a.rows, a.dtype)
     head = bn.measure(sh, owned, a.rows, a.dtype, a.batch, a.steps, a.warmup, a.verify)
+    head_check = getattr(bn, "last_check", None) if a.verify > 0 else None       # (queries, ids, distances) the oracle confirmed
     extras = []
 
     def recall_vs(got_ids, want_ids, nrq, how):
@@ -610,6 +665,10 @@ def run_ours(a):
             bn.free(shb)
     if sh is not None:
         bn.free(sh)
+    group_e2e = None
+    if world > 1 and not a.no_group_e2e:
+        chk = head_check if head_check is not None else (np.zeros((0, DIM), np.float32), [], [])
+        group_e2e = bn.group_e2e(a.rows, a.dtype, a.batch, a.steps, a.warmup, *chk)
     if world > 1:
         bn.dist.barrier()
         bn.dist.destroy_process_group()
@@ -619,9 +678,12 @@ def run_ours(a):
             "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "bf16", "data": "synthetic",
             "config": head["config"], "run": dict(head["run"], table_build_s=round(build_s, 2)),
-            "p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "latency": head.get("latency"), "e2e": head.get("e2e"),
+            "p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "latency": head.get("latency"),
+            "e2e": group_e2e if group_e2e is not None else head.get("e2e"),
             "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": head["clocks"],
             "verify": head["verify"], "fallbacks": head["fallbacks"]}
+    if group_e2e is not None:
+        line["e2e_rank_per_gpu"] = head.get("e2e")      # the same host-buffer step through orx_search_sharded on every rank
     if extras:
         line["configs"] = extras
     if not a.no_cpu_baseline and world == 1:

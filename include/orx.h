@@ -178,6 +178,14 @@ int orx_shard_connect(orx_index *idx, const void *handles, int n_handles);
 int orx_search_sharded(orx_index *idx, const float *queries, int nq, int dim, int k,
                        orx_id *out_ids, double *out_dist, int *out_counts);
 
+/* Diagnostic for the exactness argument: the COARSE scores of the tcgen05 batch scan -- the
+ * tf32 (fp32 table) or bf16 (bf16 table) tensor-core dot of every live row with every normalised query, times the
+ * row's 1/|x| -- computed by the same TMA / tcgen05.mma / TMEM pipeline as orx_search (only the epilogue writes
+ * instead of selecting; use_pairs picks the cta_group::2 kernel).  out_device [live rows, nq] fp32 in table row order
+ * (row order = orx_export_rows).  A test measures max |coarse - cosine| with it and checks it against the epsilon
+ * the completeness proof assumes.  1 <= nq <= 2048. */
+int orx_debug_coarse_scores(orx_index *idx, const float *queries, int nq, int use_pairs, float *out_device);
+
 /* Read back stored rows (as fp32) by id -- snapshot / debugging / tests.
  * out_vecs [n, dim] host; out_found [n] host (1/0). */
 int orx_fetch(orx_index *idx, const orx_id *ids, uint64_t n, float *out_vecs, int *out_found);

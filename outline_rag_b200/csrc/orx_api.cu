@@ -1611,6 +1611,25 @@ int orx_search_sharded(orx_index *ix, const float *queries, int nq, int dim, int
     return ORX_OK;
 }
 
+int orx_debug_coarse_scores(orx_index *ix, const float *queries, int nq, int use_pairs, float *out_device) {
+    if (!ix || !queries || !out_device) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return fail(ORX_ERR_INVALID, "per-GPU diagnostic: call it on a single-GPU index");
+    if (!is_device_ptr(out_device)) return fail(ORX_ERR_INVALID, "out must be device memory");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!ix->umma || ix->n_live == 0) return fail(ORX_ERR_INVALID, "empty table");
+    const float *q_src = nullptr;
+    int rc = stage_queries(ix, queries, nq, &q_src);
+    if (rc != ORX_OK) return rc;
+    rc = orx::umma_dump_scores(ix->umma, ix->dtype, ix->table, ix->scale, (uint32_t)ix->n_live, ix->qhat.p, ix->qhat16.p, nq,
+                               use_pairs != 0, out_device, ix->stream);
+    if (rc != ORX_OK) return fail(rc, "tcgen05 dump failed: %s", orx::umma_last_error());
+    ix->stats.kernel_launches += 2;
+    CK(cudaStreamSynchronize(ix->stream));
+    CK(cudaGetLastError());
+    return ORX_OK;
+}
+
 int orx_fetch(orx_index *ix, const orx_id *ids, uint64_t n, float *out_vecs, int *out_found) {
     if (!ix) return fail(ORX_ERR_INVALID, "index is null");
     if (n == 0) return ORX_OK;

@@ -270,12 +270,15 @@ __device__ __forceinline__ void coop_compact(uint64_t *list, int L, int lane, in
 // ------------------------------------------------------------------------------- epilogue
 // Shared by the 1-CTA and the 2-CTA kernels: 4 warps, thread = one query (TMEM lane), see the file
 // header.  `arrive_empty(buf)` hands accumulator buffer `buf` back to the MMA issuer.
-template <class ArriveEmpty>
+// DUMP (diagnostic instantiation behind orx_debug_coarse_scores): instead of selecting, every scaled coarse score is
+// written to dump[row * dump_ld + query], so that a test can MEASURE max |coarse - cosine| against eps.
+template <bool DUMP, class ArriveEmpty>
 __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int n_slots, uint32_t n_tiles,
                                               const float *__restrict__ scale, uint32_t n_rows, int k, float margin,
                                               uint64_t *__restrict__ partial, float *__restrict__ floor_out,
                                               uint32_t *__restrict__ gthr_all, float *s_scale, uint32_t bar_tfull,
-                                              uint32_t tmem_base, int ew, int lane, ArriveEmpty arrive_empty
+                                              uint32_t tmem_base, int ew, int lane, ArriveEmpty arrive_empty,
+                                              float *__restrict__ dump, uint32_t dump_ld
                                               ORX_DBG_PARAM) {
     const int et = ew * 32 + lane;                          // 0..127
     const int q = q_base + ew * 32 + lane;
@@ -334,6 +337,16 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
                 s[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * f.w;
                 mx = fmaxf(fmaxf(mx, fmaxf(s[4 * j4 + 0], s[4 * j4 + 1])), fmaxf(s[4 * j4 + 2], s[4 * j4 + 3]));
             }
+            if constexpr (DUMP) {
+                if (active) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const uint32_t row = n0 + c * 32 + j;
+                        if (row < n_rows) dump[(size_t)row * dump_ld + q] = s[j];      // a warp writes 32 consecutive queries
+                    }
+                }
+                continue;
+            }
             // fmaxf ignores NaN (zero-norm rows, rows beyond the end); irregular rows need the slow path
             const bool hit = active && ((mx > thr) || tile_special);
             if (!__any_sync(FULL_MASK, hit)) continue;
@@ -387,18 +400,18 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
         if (lane == 0) arrive_empty(buf);
         if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
-    if (active) {
+    if (active && !DUMP) {
         for (int i = cnt; i < CAND; ++i) buf_keys[i] = 0ull;
         floor_out[(size_t)q * n_slots + slot] = overflow ? __int_as_float(0x7f800000) : thr;
     }
 }
 
-template <bool TF32>
+template <bool TF32, bool DUMP = false>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const float *__restrict__ scale, uint32_t n_rows, int nq, int m_tiles, int n_slots, int k,
                  float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
-                 uint32_t *__restrict__ gthr_all ORX_DBG_PARAM) {
+                 uint32_t *__restrict__ gthr_all, float *__restrict__ dump, uint32_t dump_ld ORX_DBG_PARAM) {
     constexpr int ES = TF32 ? 4 : 2;                // operand element size
     constexpr int BLOCK_K = 128 / ES;               // elements per 128-byte swizzle row
     constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;     // 16 (bf16) / 32 (tf32)
@@ -488,9 +501,9 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
     } else if (warp < 4) {
         // ========================================================================= epilogue
-        epilogue_loop(m_tile * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin, partial, floor_out,
-                      gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
-                      [&](uint32_t b) { mbar_arrive(bar_tempty + 8 * b); } ORX_DBG_FWD);
+        epilogue_loop<DUMP>(m_tile * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin, partial, floor_out,
+                            gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
+                            [&](uint32_t b) { mbar_arrive(bar_tempty + 8 * b); }, dump, dump_ld ORX_DBG_FWD);
     }
 
     tc_fence_before();
@@ -509,12 +522,12 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // ring (3072 MMA cycles of prefetch instead of 2048).  Only the leader CTA issues MMAs; commits are
 // multicast to both CTAs' barriers; both CTAs' TMA bytes are counted on the leader's full barrier;
 // both CTAs' epilogues hand accumulators back by arriving on the leader's tmem-empty barrier.
-template <bool TF32>
+template <bool TF32, bool DUMP = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                   const float *__restrict__ scale, uint32_t n_rows, int nq, int m_pairs, int n_slots, int k,
                   float margin, uint64_t *__restrict__ partial, float *__restrict__ floor_out,
-                  uint32_t *__restrict__ gthr_all ORX_DBG_PARAM) {
+                  uint32_t *__restrict__ gthr_all, float *__restrict__ dump, uint32_t dump_ld ORX_DBG_PARAM) {
     constexpr int ES = TF32 ? 4 : 2;
     constexpr int BLOCK_K = 128 / ES;
     constexpr int K_CHUNKS = ORX_DIM / BLOCK_K;
@@ -612,9 +625,9 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     } else if (warp < 4) {
         // ============================================== epilogue (each CTA: its own 128 queries)
         const uint32_t tempty_leader = map_to_cta(bar_tempty, 0);
-        epilogue_loop(m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
-                      partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
-                      [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); } ORX_DBG_FWD);
+        epilogue_loop<DUMP>(m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
+                            partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
+                            [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); }, dump, dump_ld ORX_DBG_FWD);
     }
 
     tc_fence_before();
@@ -711,6 +724,28 @@ bool umma_should_use(const UmmaPlan *p, int nq, uint32_t n_rows) {
     return p != nullptr && nq >= 2 && n_rows >= 4096;     // (k <= 32 is checked by the caller: 64-slot lists)
 }
 
+static bool ensure_attrs(UmmaPlan *p) {
+    if (p->attr_set) return true;
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void *fn, int bytes) {
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    };
+    set((const void *)scan_umma_kernel<true, false>, SMEM_TOTAL);
+    set((const void *)scan_umma_kernel<false, false>, SMEM_TOTAL);
+    set((const void *)scan_umma_kernel<true, true>, SMEM_TOTAL);
+    set((const void *)scan_umma_kernel<false, true>, SMEM_TOTAL);
+    set((const void *)scan_umma2_kernel<true, false>, SMEM2_TOTAL);
+    set((const void *)scan_umma2_kernel<false, false>, SMEM2_TOTAL);
+    set((const void *)scan_umma2_kernel<true, true>, SMEM2_TOTAL);
+    set((const void *)scan_umma2_kernel<false, true>, SMEM2_TOTAL);
+    if (e != cudaSuccess) {
+        g_umma_err = cudaGetErrorString(e);
+        return false;
+    }
+    p->attr_set = true;
+    return true;
+}
+
 template <typename T>
 static cudaError_t ensure_buf(T *&ptr, size_t &have, size_t want) {
     if (want <= have) return cudaSuccess;
@@ -730,17 +765,7 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
     const bool tf32 = dtype == ORX_DTYPE_F32;
     const double eps = tf32 ? EPS_UMMA_TF32 : EPS_UMMA_BF16;
     const float margin = (float)(2.0 * eps + 1e-6);
-    if (!p->attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(scan_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(scan_umma2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(scan_umma2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2_TOTAL);
-        if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
-        p->attr_set = true;
-    }
+    if (!ensure_attrs(p)) return ORX_ERR_CUDA;
     constexpr int MAX_Q = 2048;              // 16 query tiles -> 9 row slots -> 144 CTAs
     for (int q0 = 0; q0 < nq; q0 += MAX_Q) {
         const int m = nq - q0 < MAX_Q ? nq - q0 : MAX_Q;
@@ -766,18 +791,18 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
             const int grid = 2 * m_tiles * n_slots;
             if (tf32)
                 scan_umma2_kernel<true><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                               k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
+                                                                               k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
             else
                 scan_umma2_kernel<false><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                                k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
+                                                                                k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
         } else {
             const int grid = m_tiles * n_slots;
             if (tf32)
                 scan_umma_kernel<true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                             k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
+                                                                             k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
             else
                 scan_umma_kernel<false><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                              k, margin, p->partial, p->floor, p->gthr ORX_DBG_ARG(p));
+                                                                              k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
         }
         if (ev_end && q0 + MAX_Q >= nq) cudaEventRecord(ev_end, st);
         launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, 2, m,
@@ -789,6 +814,42 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
         e = cudaGetLastError();
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
     }
+    return ORX_OK;
+}
+
+// Diagnostic: the scaled coarse scores of the tcgen05 pass, out[row * nq + query] (device memory, [n_rows, nq] fp32), through
+// the SAME TMA / UMMA / TMEM path as the search (only the epilogue differs: it writes instead of selecting).
+int umma_dump_scores(UmmaPlan *p, int dtype, const void *table, const float *scale, uint32_t n_rows, const float *qhat,
+                     const __nv_bfloat16 *qhat16, int nq, bool pairs, float *out, cudaStream_t st) {
+    const bool tf32 = dtype == ORX_DTYPE_F32;
+    if (!ensure_attrs(p)) return ORX_ERR_CUDA;
+    if (nq < 1 || nq > 2048) { g_umma_err = "1..2048 queries"; return ORX_ERR_INVALID; }
+    const int m_tiles = pairs ? (nq + 2 * TILE_M - 1) / (2 * TILE_M) : (nq + TILE_M - 1) / TILE_M;
+    const uint32_t n_tiles = (n_rows + TILE_N - 1) / TILE_N;
+    int n_slots = (pairs ? p->sms / 2 : p->sms) / m_tiles;
+    if (n_slots < 1) n_slots = 1;
+    if ((uint32_t)n_slots > n_tiles) n_slots = (int)n_tiles;
+    CUtensorMap map_q, map_x;
+    const void *qbase = tf32 ? (const void *)qhat : (const void *)qhat16;
+    if (!encode_map(&map_q, qbase, (uint64_t)((nq + 255) / 256 * 256), tf32, TILE_M)) return ORX_ERR_CUDA;
+    if (!encode_map(&map_x, table, (uint64_t)n_rows, tf32, pairs ? TILE_N / 2 : TILE_N)) return ORX_ERR_CUDA;
+    // the selection state is unused in DUMP mode but the kernel signature wants valid pointers
+    cudaError_t e = ensure_buf(p->partial, p->partial_n, (size_t)nq * n_slots * CAND);
+    if (e == cudaSuccess) e = ensure_buf(p->floor, p->floor_n, (size_t)nq * n_slots);
+    if (e == cudaSuccess) e = ensure_buf(p->gthr, p->gthr_n, (size_t)nq);
+    if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
+    cudaMemsetAsync(p->gthr, 0, (size_t)nq * sizeof(uint32_t), st);
+    if (pairs) {
+        const int grid = 2 * m_tiles * n_slots;
+        if (tf32) scan_umma2_kernel<true, true><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, nq, m_tiles, n_slots, 12, 0.f, p->partial, p->floor, p->gthr, out, (uint32_t)nq ORX_DBG_ARG(p));
+        else scan_umma2_kernel<false, true><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, nq, m_tiles, n_slots, 12, 0.f, p->partial, p->floor, p->gthr, out, (uint32_t)nq ORX_DBG_ARG(p));
+    } else {
+        const int grid = m_tiles * n_slots;
+        if (tf32) scan_umma_kernel<true, true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, nq, m_tiles, n_slots, 12, 0.f, p->partial, p->floor, p->gthr, out, (uint32_t)nq ORX_DBG_ARG(p));
+        else scan_umma_kernel<false, true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, nq, m_tiles, n_slots, 12, 0.f, p->partial, p->floor, p->gthr, out, (uint32_t)nq ORX_DBG_ARG(p));
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
     return ORX_OK;
 }
 

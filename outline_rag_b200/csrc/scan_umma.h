@@ -22,4 +22,8 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
                 const PublishArgs &pub, const DoneArgs &done, cudaStream_t st,
                 uint64_t *launch_counter, cudaEvent_t ev_begin, cudaEvent_t ev_end);
 
+// diagnostic: every scaled coarse score of the tcgen05 pass, out[row * nq + query] (device), same MMA path as the search
+int umma_dump_scores(UmmaPlan *p, int dtype, const void *table, const float *scale, uint32_t n_rows, const float *qhat,
+                     const __nv_bfloat16 *qhat16, int nq, bool pairs, float *out, cudaStream_t st);
+
 }  // namespace orx

@@ -321,6 +321,16 @@ class Index:
                              C.c_void_p(dist.ctypes.data), C.c_void_p(cnt.ctypes.data)))
         return ids, dist, cnt
 
+    def debug_coarse_scores(self, queries, use_pairs: bool = False):
+        """Diagnostic (`orx_debug_coarse_scores`): float32 CUDA tensor [live rows, nq] of the tcgen05 pass's coarse
+        scores, rows in table order."""
+        q = _host_f32(queries, "queries") if not _is_cuda_tensor(queries) else queries.contiguous()
+        nq = q.shape[0]
+        out = torch.empty((len(self), nq), dtype=torch.float32, device=f"cuda:{self.device}")
+        ptr = q.data_ptr() if _is_cuda_tensor(q) else q.ctypes.data
+        check(lib.orx_debug_coarse_scores(self._h, C.c_void_p(ptr), nq, int(bool(use_pairs)), C.c_void_p(out.data_ptr())))
+        return out
+
     def make_filter(self, allow_ids) -> Filter:
         return Filter(self, allow_ids)
 
