@@ -95,6 +95,9 @@ int orx_set_option(orx_index *idx, int option, int value);
 uint64_t orx_size(const orx_index *idx);       /* live rows */
 uint64_t orx_capacity(const orx_index *idx);
 int orx_dtype(const orx_index *idx);
+/* Changes with every successful write (upsert, delete, import).  A snapshot taken in several orx_export_rows calls is
+ * consistent iff this value is the same before the first and after the last call (Index.save checks it). */
+uint64_t orx_mutation_count(const orx_index *idx);
 int orx_get_stats(const orx_index *idx, orx_stats *out);
 
 /* Replaces `vector_store.aadd_documents(chunks)` -> per-row

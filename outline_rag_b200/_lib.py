@@ -82,6 +82,7 @@ SIGNATURES = {
     "orx_size": (C.c_uint64, [_vp]),
     "orx_capacity": (C.c_uint64, [_vp]),
     "orx_dtype": (C.c_int, [_vp]),
+    "orx_mutation_count": (C.c_uint64, [_vp]),
     "orx_get_stats": (C.c_int, [_vp, C.POINTER(OrxStats)]),
     "orx_upsert": (C.c_int, [_vp, _vp, _vp, C.c_uint64, C.c_int]),
     "orx_delete": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),

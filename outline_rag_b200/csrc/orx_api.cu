@@ -162,6 +162,7 @@ struct orx_index {
     uint64_t capacity = 0;
     uint64_t n_live = 0;
     uint64_t generation = 0;            // bumped whenever the id -> row map changes (orx_filter re-resolves then)
+    std::atomic<uint64_t> mutations{0}; // bumped by EVERY successful write (upsert incl. in-place, delete, import): snapshots check it
     int scan_grid_sms = 0;              // multiProcessorCount of `device` (orx_create)
 
     // the table (device)
@@ -408,6 +409,7 @@ int upsert_locked(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t 
             ix->n_live = next_row;
             ix->generation += 1;
         }
+        ix->mutations.fetch_add(1);
     }
     return ORX_OK;
 }
@@ -1218,6 +1220,16 @@ uint64_t orx_capacity(const orx_index *ix) {
 }
 int orx_dtype(const orx_index *ix) { return ix ? ix->dtype : -1; }
 
+uint64_t orx_mutation_count(const orx_index *ix) {
+    if (!ix) return 0;
+    if (ix->group) {
+        uint64_t m = 0;
+        for (orx_index *s : ix->group->shards) m += s->mutations.load();
+        return m;
+    }
+    return ix->mutations.load();
+}
+
 int orx_get_stats(const orx_index *ix, orx_stats *out) {
     if (!ix || !out) return fail(ORX_ERR_INVALID, "null argument");
     if (ix->group) return group_stats(ix->group, out);
@@ -1289,6 +1301,7 @@ int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed
     ix->host_row_ids.resize(new_live);
     ix->n_live = new_live;
     ix->generation += 1;
+    ix->mutations.fetch_add(1);
     if (hmv > 0) {
         CK(ix->d_src_idx.ensure(hmv));
         CK(ix->d_dst_row.ensure(hmv));
@@ -1509,6 +1522,7 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
     }
     ix->n_live = row0 + n;
     ix->generation += 1;
+    ix->mutations.fetch_add(1);
     return ORX_OK;
 }
 

@@ -12,10 +12,15 @@ server's `QueryBatcher` into one tcgen05 scan -- cross-process micro-batching fo
 Writes are applied in arrival order on the owner's single stream, so a search issued after an
 upsert was acknowledged sees it (same guarantee as in-process use).
 
-Wire format: 4-byte big-endian length + msgpack map {"op", ...}; arrays travel as raw bytes with
-shape / dtype fields.  Errors come back as {"err": code, "msg": text} and are re-raised as
-`OrxError` / `OrxValueError` on the client, so `api.py:125-127`'s "log and return no documents"
-behaviour is unchanged.
+Wire format: 4-byte big-endian length + msgpack map {"op", "rid", ...}; arrays travel as raw bytes with
+shape / dtype fields; every response echoes the request id ("rid").  Errors come back as
+{"err": code, "msg": text} and are re-raised as `OrxError` / `OrxValueError` on the client, so
+`api.py:125-127`'s "log and return no documents" behaviour is unchanged.
+
+The client keeps a small POOL of connections: concurrent searches of one worker travel on different connections (so
+the owner's batcher can coalesce them too), and a connection on which anything went wrong -- a timeout, a partial
+read, a decode error, a response whose id is not the request's -- is CLOSED and never reused: a later caller can never
+read the tail of somebody else's response.
 """
 from __future__ import annotations
 
@@ -89,6 +94,7 @@ class IndexServer:
                 req = msgpack.unpackb(body, raw=False)
                 # requests of one connection are answered in order; different connections interleave
                 resp = await self._handle(req)
+                resp["rid"] = req.get("rid")
                 out = msgpack.packb(resp, use_bin_type=True)
                 writer.write(struct.pack(">I", len(out)) + out)
                 await writer.drain()
@@ -170,41 +176,82 @@ class ServerThread(threading.Thread):
 
 
 # --------------------------------------------------------------------------------- client
-class RemoteIndex:
-    """`Index`-shaped proxy used by a worker process: blocking calls over one unix socket
-    (thread-safe; `GpuVectorStore` already runs index calls in `asyncio.to_thread`)."""
-
-    def __init__(self, path: str, timeout: float = 60.0):
-        self.path = path
-        self._sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        self._sock.settimeout(timeout)
-        self._sock.connect(path)
-        self._lock = threading.Lock()
+class _Conn:
+    def __init__(self, path: str, timeout: float):
+        self.sock = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        self.sock.settimeout(timeout)
+        self.sock.connect(path)
 
     def close(self) -> None:
         try:
-            self._sock.close()
+            self.sock.close()
         except OSError:
             pass
 
-    def _call(self, req: dict) -> dict:
-        out = msgpack.packb(req, use_bin_type=True)
-        with self._lock:
-            self._sock.sendall(struct.pack(">I", len(out)) + out)
-            head = self._recv(4)
-            resp = msgpack.unpackb(self._recv(struct.unpack(">I", head)[0]), raw=False)
-        if "err" in resp:
-            _raise_from(resp)
-        return resp
-
-    def _recv(self, n: int) -> bytes:
+    def recv_exact(self, n: int) -> bytes:
         buf = bytearray()
         while len(buf) < n:
-            chunk = self._sock.recv(n - len(buf))
+            chunk = self.sock.recv(n - len(buf))
             if not chunk:
                 raise OrxError(-100, "index server closed the connection")
             buf += chunk
         return bytes(buf)
+
+
+class RemoteIndex:
+    """`Index`-shaped proxy used by a worker process: blocking calls over a pool of unix-socket connections
+    (thread-safe; `GpuVectorStore` already runs index calls in `asyncio.to_thread`)."""
+
+    def __init__(self, path: str, timeout: float = 60.0, max_connections: int = 8):
+        self.path, self.timeout = path, timeout
+        self._idle: list[_Conn] = [_Conn(path, timeout)]          # fail at construction if the owner is not there
+        self._lock = threading.Lock()
+        self._slots = threading.BoundedSemaphore(max_connections)
+        self._rid = 0
+        self._closed = False
+
+    def close(self) -> None:
+        with self._lock:
+            self._closed = True
+            idle, self._idle = self._idle, []
+        for c in idle:
+            c.close()
+
+    def _call(self, req: dict) -> dict:
+        with self._slots:
+            with self._lock:
+                if self._closed:
+                    raise OrxError(-100, "RemoteIndex is closed")
+                self._rid += 1
+                rid = self._rid
+                conn = self._idle.pop() if self._idle else None
+            if conn is None:
+                conn = _Conn(self.path, self.timeout)
+            ok = False
+            try:
+                out = msgpack.packb(dict(req, rid=rid), use_bin_type=True)
+                conn.sock.sendall(struct.pack(">I", len(out)) + out)
+                head = conn.recv_exact(4)
+                resp = msgpack.unpackb(conn.recv_exact(struct.unpack(">I", head)[0]), raw=False)
+                if not isinstance(resp, dict) or resp.get("rid") != rid:
+                    raise OrxError(-100, "index server answered another request (framing lost): connection dropped")
+                ok = True
+            except OrxError:
+                raise
+            except Exception as e:       # noqa: BLE001 -- timeout, reset, decode error: the stream position is unknown
+                raise OrxError(-100, f"index server call failed ({type(e).__name__}: {e}): connection dropped") from e
+            finally:
+                if ok:
+                    with self._lock:
+                        if self._closed:
+                            conn.close()
+                        else:
+                            self._idle.append(conn)
+                else:
+                    conn.close()             # never reused: the next caller gets a fresh connection
+        if "err" in resp:
+            _raise_from(resp)
+        return resp
 
     def __len__(self) -> int:
         return int(self._call({"op": "size"})["size"])

@@ -399,30 +399,55 @@ class Index:
         check(lib.orx_export_rows(self._h, int(row_start), int(n), C.c_void_p(ids_out.ctypes.data),
                                   C.c_void_p(rows_out.ctypes.data)))
 
-    def save(self, path: str) -> dict:
-        """Write `manifest.json`, `ids.bin` (uint64 [n,2]) and `vecs.bin` (rows verbatim in the table
-        dtype) under `path`.  Postgres stays the source of truth; this avoids re-loading 41 GB of
-        vectors through SQL text on restart."""
+    def save(self, path: str, retries: int = 3) -> dict:
+        """Write `manifest.json`, `ids.npy` (uint64 [n,2]) and `vecs.npy` (rows verbatim in the table dtype, uint8
+        [n, row_bytes]) under `path`.  Postgres stays the source of truth; this avoids re-loading 41 GB of vectors
+        through SQL text on restart.
+
+        The snapshot is CONSISTENT and ATOMIC: the export runs in chunks (searches and writes of other threads are not
+        locked out), the index's mutation counter is read before and after, and a snapshot during which a write
+        landed is discarded and retried (`retries` times, then `OrxError`); files are written into a temporary
+        sibling directory that replaces `path` with one rename, so a crash leaves either the old snapshot or the new
+        one, never a mixture."""
         import json
         import os
-        os.makedirs(path, exist_ok=True)
-        n = len(self)
+        import shutil
+        path = os.path.abspath(path)
+        tmp = f"{path}.tmp-{os.getpid()}"
         rb = ORX_DIM * (4 if self.dtype == "fp32" else 2)
-        manifest = {"format": "orx-snapshot-1", "dtype": self.dtype, "dim": ORX_DIM, "rows": n, "row_bytes": rb}
-        ids = np.lib.format.open_memmap(os.path.join(path, "ids.npy"), mode="w+", dtype=np.uint64, shape=(n, 2))
-        vecs = np.lib.format.open_memmap(os.path.join(path, "vecs.npy"), mode="w+", dtype=np.uint8, shape=(n, rb))
-        for s in range(0, n, self.SNAPSHOT_CHUNK):
-            m = min(self.SNAPSHOT_CHUNK, n - s)
-            ci = np.empty((m, 2), np.uint64)
-            cv = np.empty((m, rb), np.uint8)
-            check(lib.orx_export_rows(self._h, s, m, C.c_void_p(ci.ctypes.data), C.c_void_p(cv.ctypes.data)))
-            ids[s:s + m] = ci
-            vecs[s:s + m] = cv
-        ids.flush()
-        vecs.flush()
-        with open(os.path.join(path, "manifest.json"), "w") as f:
-            json.dump(manifest, f)
-        return manifest
+        for _attempt in range(max(1, retries)):
+            shutil.rmtree(tmp, ignore_errors=True)
+            os.makedirs(tmp)
+            m0 = int(lib.orx_mutation_count(self._h))
+            n = len(self)
+            manifest = {"format": "orx-snapshot-1", "dtype": self.dtype, "dim": ORX_DIM, "rows": n, "row_bytes": rb}
+            ids = np.lib.format.open_memmap(os.path.join(tmp, "ids.npy"), mode="w+", dtype=np.uint64, shape=(n, 2))
+            vecs = np.lib.format.open_memmap(os.path.join(tmp, "vecs.npy"), mode="w+", dtype=np.uint8, shape=(n, rb))
+            ok = True
+            try:
+                for s in range(0, n, self.SNAPSHOT_CHUNK):
+                    m = min(self.SNAPSHOT_CHUNK, n - s)
+                    ci = np.empty((m, 2), np.uint64)
+                    cv = np.empty((m, rb), np.uint8)
+                    check(lib.orx_export_rows(self._h, s, m, C.c_void_p(ci.ctypes.data), C.c_void_p(cv.ctypes.data)))
+                    ids[s:s + m] = ci
+                    vecs[s:s + m] = cv
+            except OrxError:
+                ok = False                       # a concurrent delete shrank the table under the export
+            ids.flush()
+            vecs.flush()
+            del ids, vecs
+            if ok and int(lib.orx_mutation_count(self._h)) == m0 and len(self) == n:
+                with open(os.path.join(tmp, "manifest.json"), "w") as f:
+                    json.dump(manifest, f)
+                old = f"{path}.old-{os.getpid()}"
+                if os.path.exists(path):
+                    os.replace(path, old)
+                os.replace(tmp, path)
+                shutil.rmtree(old, ignore_errors=True)
+                return manifest
+        shutil.rmtree(tmp, ignore_errors=True)
+        raise OrxError(_lib.ORX_ERR_INVALID, "the index kept changing while the snapshot was taken; pause the writer or retry")
 
     @classmethod
     def load(cls, path: str, device: int | None = None, capacity: int = 0) -> "Index":

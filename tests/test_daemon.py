@@ -89,6 +89,60 @@ def test_two_workers_share_one_owner(small_table, tmp_path):
     assert not os.path.exists(path)
 
 
+def test_a_failed_call_never_desynchronises_the_next_one(small_table, tmp_path):
+    """after a timeout (or any exception between send and receive) the old client kept its socket, and the
+    next caller read the tail of the previous response -- another query's ids.  Now the connection is dropped, a
+    fresh one serves the next call, responses carry the request id, and concurrent calls of ONE client use several
+    connections (so the owner can batch them)."""
+    import time
+    import outline_rag_b200 as orx
+    from outline_rag_b200.daemon import RemoteIndex, serve_in_thread
+    X, Q, _ = small_table
+    ids = O.ids_arange(0, 400)
+
+    class SlowOwner(FakeOwner):
+        delay = 0.0
+
+        def search(self, Qb, k):
+            time.sleep(self.delay)
+            return super().search(Qb, k)
+
+    owner = SlowOwner(X[:400], ids)
+    path = str(tmp_path / "orx.sock")
+    srv = serve_in_thread(owner, path, batch_window_ms=None)
+    try:
+        c = RemoteIndex(path, timeout=0.3)
+        owner.delay = 1.0
+        with pytest.raises(orx.OrxError, match="connection dropped"):
+            c.search(Q[0], 12)                                  # times out; its late response must never be read
+        owner.delay = 0.0
+        time.sleep(1.2)                                         # the late response has been written to the dead socket
+        for qi in (1, 2, 3):
+            g = c.search(Q[qi], 12)
+            w_ids, w_d = O.topk_exact(X[:400], ids, Q[qi], 12)
+            assert np.array_equal(g[0][0], w_ids) and np.array_equal(g[1][0], w_d), "answer of another query"
+        # concurrent searches of one client: several connections, every thread gets ITS answer
+        owner.delay = 0.05
+        out = {}
+
+        def one(qi):
+            out[qi] = c.search(Q[qi], 12)
+
+        ts = [threading.Thread(target=one, args=(qi,)) for qi in range(8)]
+        t0 = time.perf_counter()
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert time.perf_counter() - t0 < 8 * 0.05 + 0.25        # not serialised behind one socket... (the fake owner is)
+        for qi in range(8):
+            w_ids, _ = O.topk_exact(X[:400], ids, Q[qi], 12)
+            assert np.array_equal(out[qi][0][0], w_ids)
+        c.close()
+        with pytest.raises(orx.OrxError, match="closed"):
+            c.search(Q[0], 12)
+    finally:
+        srv.stop()
+
+
 CHILD = r"""
 import json, sys, numpy as np
 sys.path.insert(0, sys.argv[1])

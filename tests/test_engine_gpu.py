@@ -484,6 +484,45 @@ def test_snapshot_roundtrip_is_bit_identical(Index, small_table, tmp_path, dtype
         orx.Index.load(str(tmp_path / "snap"))
 
 
+def test_snapshot_is_atomic_and_refuses_a_table_that_changes_under_it(Index, small_table, tmp_path, monkeypatch):
+    """`save` exported in chunks with the lock released in between and overwrote the files in place.  Now
+    it writes beside the target and renames, and it notices a write that lands between two chunks (mutation counter)."""
+    import os
+    import outline_rag_b200 as orx
+    from outline_rag_b200 import engine as E
+    X, Q, _ = small_table
+    ids = _ids(3000)
+    snap = str(tmp_path / "snap")
+    with Index("fp32") as a:
+        a.upsert(ids, X[:3000])
+        a.save(snap)
+        a.delete(ids[:100])
+        man = a.save(snap)                                      # replaces the older snapshot in one rename
+        assert man["rows"] == 2900 and sorted(os.listdir(tmp_path)) == ["snap"]
+        with orx.Index.load(snap) as b:
+            assert len(b) == 2900 and not b.contains(5)
+        # a writer slips in between two export chunks: the half-taken snapshot is discarded, the old one survives
+        monkeypatch.setattr(E.Index, "SNAPSHOT_CHUNK", 1000)
+        real = E.lib.orx_export_rows
+        calls = {"n": 0}
+
+        def export_and_write(*args):
+            calls["n"] += 1
+            rc = real(*args)
+            if calls["n"] % 2 == 1:
+                a.upsert(_ids(1, 900_000 + calls["n"]), X[4000:4001])       # every attempt sees a new write
+            return rc
+
+        monkeypatch.setattr(E.lib, "orx_export_rows", export_and_write)
+        with pytest.raises(orx.OrxError, match="kept changing"):
+            a.save(snap, retries=2)
+        monkeypatch.setattr(E.lib, "orx_export_rows", real)
+        assert sorted(os.listdir(tmp_path)) == ["snap"]
+        with orx.Index.load(snap) as b:
+            assert len(b) == 2900                               # still the last GOOD snapshot
+        assert a.save(snap)["rows"] == len(a)
+
+
 def test_concurrent_threads_search_while_a_writer_refreshes(Index, small_table):
     """The uvicorn worker runs searches and the refresh task interleaved (asyncio.to_thread): calls on one
     index are serialised, every search sees a consistent table (either before or after a whole batch)."""
