@@ -359,7 +359,7 @@ class Bench:
     # -------------------------------------------------------------- table
     def build(self, rows, dtype):
         from outline_rag_b200.sharded import ShardedIndex
-        cap = rows // self.world + rows // (self.world * 8) + 4096 if self.world > 1 else rows
+        cap = rows // self.world + rows // (self.world * 8) + 4096 if self.world > 1 else rows + 65_536
         sh = ShardedIndex(dtype, cap, self.local)
         sh.local.use_torch_stream()
         t0 = time.perf_counter()
@@ -630,15 +630,23 @@ def run_ours(a):
             extras.append(r)
         return r
 
-    if extras_on and a.dtype == "fp32":
+    sh_box = [sh]
+
+    def run_extras():
+        sh = sh_box[0]
         from orx_testkit.synth import Synth, default_centres
         nrq = a.recall_queries
         Qr = torch.from_numpy(Synth(default_centres(a.rows)).queries(nrq, a.rows)[0]).cuda()
         # ---- the fp32 table that is resident: batch 64 (tf32 tcgen05 scan, one table pass for 64 queries)
         extra(sh, owned, a.rows, "fp32", 64, 30, verify_n=4)
         recall_ref = step_out_to_host(sh.search(Qr, K))[0][:, :, 1].copy()        # fp32 answers for recall@12
+        if world == 1:
+            # ---- BASELINE.json configs[4]: the refresh writer interleaved with single-query searches (mutates the table)
+            r = mixed_on(sh.local, a.rows, "fp32", 6)
+            r["run"] = {"rows_per_gpu": owned, "parallelism": "row-shard x1", "exchange": "none"}
+            extras.append(r)
         bn.free(sh)
-        sh = None
+        sh_box[0] = None
         # ---- the same rows as a bf16 table
         shb, ownedb, _ = bn.build(a.rows, "bf16")
         for B, st, vn in ((1, 60, 0), (256, 20, 0), (1024, 12, 4)):
@@ -663,66 +671,101 @@ def run_ours(a):
                 r["recall"] = recall_vs(got, ref, nrq, "ids of the bf16 table vs an fp32 twin of the same 100M rows")
                 r["run"]["table_build_s"] = round(build_big, 2)
             bn.free(shb)
-    if sh is not None:
-        bn.free(sh)
+    # ---- the headline is complete once the one-process multi-GPU leg has run (the rank tables may stay resident:
+    #      10M rows are 41 GB in total)
     group_e2e = None
     if world > 1 and not a.no_group_e2e:
         chk = head_check if head_check is not None else (np.zeros((0, DIM), np.float32), [], [])
         group_e2e = bn.group_e2e(a.rows, a.dtype, a.batch, a.steps, a.warmup, *chk)
+
+    def headline_line():
+        line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "bf16", "data": "synthetic",
+                "config": head["config"], "run": dict(head["run"], table_build_s=round(build_s, 2)),
+                "p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "latency": head.get("latency"),
+                "e2e": group_e2e if group_e2e is not None else head.get("e2e"),
+                "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": head["clocks"],
+                "verify": head["verify"], "fallbacks": head["fallbacks"]}
+        if group_e2e is not None:
+            line["e2e_rank_per_gpu"] = head.get("e2e")      # the same host-buffer step through orx_search_sharded on every rank
+        return line
+
+    # ---- the other BASELINE configurations.  They must never cost the headline line: a watchdog prints it and ends the
+    #      process if they hang, an exception ends them early.
+    printed = threading.Lock()
+
+    def emit(line):
+        if printed.acquire(blocking=False):
+            if rank == 0:
+                print(json.dumps(line), flush=True)
+            return True
+        return False
+
+    def emergency(why):
+        if rank == 0:
+            line = headline_line()
+            if extras:
+                line["configs"] = list(extras)
+            line["configs_error"] = why
+            emit(line)
+        sys.stdout.flush()
+        os._exit(0)
+
+    watchdog = None
+    if extras_on and a.dtype == "fp32":
+        watchdog = threading.Timer(600.0 if world > 1 else 400.0, emergency, args=("the extra configurations ran out of time",))
+        watchdog.daemon = True
+        watchdog.start()
+        try:
+            run_extras()
+        except Exception as e:      # noqa: BLE001 -- whatever happened, the headline line is printed
+            emergency(f"{type(e).__name__}: {str(e)[:300]}")
+        watchdog.cancel()
+    if sh_box[0] is not None:
+        bn.free(sh_box[0])
     if world > 1:
         bn.dist.barrier()
         bn.dist.destroy_process_group()
     if rank != 0:
         return
-    line = {"metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "bf16", "data": "synthetic",
-            "config": head["config"], "run": dict(head["run"], table_build_s=round(build_s, 2)),
-            "p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "latency": head.get("latency"),
-            "e2e": group_e2e if group_e2e is not None else head.get("e2e"),
-            "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": head["clocks"],
-            "verify": head["verify"], "fallbacks": head["fallbacks"]}
-    if group_e2e is not None:
-        line["e2e_rank_per_gpu"] = head.get("e2e")      # the same host-buffer step through orx_search_sharded on every rank
+    line = headline_line()
     if extras:
         line["configs"] = extras
     if not a.no_cpu_baseline and world == 1:
         cb = time_cpu_arm(a.rows, a.batch, 20, 3)
         cb.pop("_lat_measured", None)
         line["cpu_baseline"] = cb
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
-def run_mixed(a):
-    """BASELINE.json configs[4]: the webhook refresh (reference app/rag.py:216-235: look up the old chunk
-    ids of REFRESH_BATCH_SIZE=50 docs, `adelete` them, `aadd_documents` the re-chunked rows) interleaved
-    with top-12 queries.  One round = delete(~1000 ids) + upsert(~1000 rows, host buffers) + 100 searches."""
+def mixed_on(ix, rows, dtype, rounds):
+    """BASELINE.json configs[4] on a table that is already built: the webhook refresh (reference app/rag.py:216-235:
+    look up the old chunk ids of REFRESH_BATCH_SIZE=50 docs, `adelete` them, `aadd_documents` the re-chunked rows)
+    interleaved with top-12 queries.  One round = delete(~1000 ids) + upsert(~1000 rows, host buffers) + 100 searches
+    (host buffers through the C-ABI).  Returns the result dict; the table keeps its size (old chunks out, new in)."""
     import torch
     import outline_rag_b200 as orx
     from orx_testkit.synth import Synth, default_centres, doc_chunk_counts
-    torch.cuda.set_device(0)
-    ix = orx.Index(a.dtype, a.rows + 200_000, 0)
-    ix.use_torch_stream()
-    build_table(ix.upsert, 0, a.rows, 0, 1)
-    syn = Synth(default_centres(a.rows))
-    Qh, _ = syn.queries(128, a.rows)
+    syn = Synth(default_centres(rows))
+    Qh, _ = syn.queries(128, rows)
     # documents = consecutive runs of 8..40 chunk ids (mean ~20) over the initial table
-    counts = doc_chunk_counts(a.rows // 16)
+    counts = doc_chunk_counts(rows // 16)
     starts = np.concatenate([[0], np.cumsum(counts)])
-    n_docs = int(np.searchsorted(starts, a.rows, side="right") - 1)
+    n_docs = int(np.searchsorted(starts, rows, side="right") - 1)
     rng = np.random.default_rng(20261020)
     order = rng.permutation(n_docs)
     docs_per_batch, searches_per_round = orx.REFRESH_BATCH_SIZE, 100
-    next_id = a.rows
-    rounds = []
-    for r in range(a.mixed_rounds + 2):
+    next_id = rows + 1_000_000_000
+    plan = []
+    for r in range(rounds + 2):
         docs = order[r * docs_per_batch:(r + 1) * docs_per_batch]
         old_ids = np.concatenate([np.arange(starts[d], starts[d + 1]) for d in docs]).astype(np.uint64)
         n_new = int(counts[docs].sum())                       # re-chunked: same sizes, new uuids, new embeddings
         new_ids = np.arange(next_id, next_id + n_new, dtype=np.uint64)
         new_vecs = syn.rows(new_ids)                          # stands in for the remote embedding service
         next_id += n_new
-        rounds.append((old_ids, new_ids, new_vecs))
+        plan.append((old_ids, new_ids, new_vecs))
 
     def search_loop(n, lat):
         for i in range(n):
@@ -730,21 +773,22 @@ def run_mixed(a):
             ix.search(Qh[i % 128:i % 128 + 1], K)
             lat.append(time.perf_counter() - t)
 
+    n0 = len(ix)
     lat_idle = []
-    search_loop(200, [])
+    search_loop(50, [])
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    search_loop(a.mixed_rounds * searches_per_round, lat_idle)
+    search_loop(rounds * searches_per_round, lat_idle)
     idle_s = time.perf_counter() - t0
 
     lat_mixed, t_del, t_up = [], [], []
-    s0 = ix.stats()
-    for old_ids, new_ids, new_vecs in rounds[:2]:             # warm-up rounds (buffers, maps)
+    for old_ids, new_ids, new_vecs in plan[:2]:               # warm-up rounds (buffers, maps)
         ix.delete(old_ids); ix.upsert(new_ids, new_vecs); search_loop(10, [])
     torch.cuda.synchronize()
+    s0 = ix.stats()
     t0 = time.perf_counter()
     n_rows_written = 0
-    for old_ids, new_ids, new_vecs in rounds[2:]:
+    for old_ids, new_ids, new_vecs in plan[2:]:
         t = time.perf_counter(); removed = ix.delete(old_ids); t_del.append(time.perf_counter() - t)
         assert removed == len(old_ids)
         t = time.perf_counter(); ix.upsert(new_ids, new_vecs); t_up.append(time.perf_counter() - t)
@@ -753,35 +797,48 @@ def run_mixed(a):
     torch.cuda.synchronize()
     mixed_s = time.perf_counter() - t0
     s1 = ix.stats()
-    assert len(ix) == a.rows
+    assert len(ix) == n0
     # deleted chunks never come back, new ones are searchable
-    probe = rounds[-1][2][:4]
-    got = ix.search(probe, 1)[0][:, 0, 1]
-    ok = bool((got == rounds[-1][1][:4]).all())
-    n_search = a.mixed_rounds * searches_per_round
-    line = {"metric": METRIC + "_mixed", "value": n_search / mixed_s, "unit": UNIT, "n_gpus": 1,
-            "steps": n_search, "warmup": 220, "ms_per_step": mixed_s / n_search * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "bf16",
-            "data": "synthetic",
-            "config": {"workload": f"mixed: per round delete+upsert of {docs_per_batch} docs (~{n_rows_written // a.mixed_rounds} "
-                                   f"rows) then {searches_per_round} single-query top-{K} searches, {a.rows}x{DIM} {a.dtype}",
-                       "rounds": a.mixed_rounds},
+    got = ix.search(plan[-1][2][:4], 1)[0][:, 0, 1]
+    ok = bool((got == plan[-1][1][:4]).all())
+    gone = ix.search(syn.rows(plan[-1][0][:4]), 1)[0][:, 0, 1]
+    ok &= bool((gone != plan[-1][0][:4]).all())
+    n_search = rounds * searches_per_round
+    return {"config": {"workload": f"mixed: per round delete+upsert of {docs_per_batch} docs (~{n_rows_written // rounds} rows) "
+                                   f"then {searches_per_round} single-query top-{K} searches, {rows}x{DIM} {dtype}",
+                       "rows": rows, "dim": DIM, "k": K, "batch": 1, "table_dtype": dtype, "rounds": rounds},
+            "value": n_search / mixed_s, "unit": UNIT, "steps": n_search, "ms_per_step": mixed_s / n_search * 1e3,
             "search_only": {"qps": n_search / idle_s, "p50_ms": float(np.median(lat_idle) * 1e3),
                             "p99_ms": float(np.percentile(lat_idle, 99) * 1e3)},
             "with_writer": {"qps": n_search / mixed_s, "p50_ms": float(np.median(lat_mixed) * 1e3),
-                            "p99_ms": float(np.percentile(lat_mixed, 99) * 1e3),
+                            "p99_ms": float(np.percentile(lat_mixed, 99) * 1e3), "max_ms": float(np.max(lat_mixed) * 1e3),
                             "delete_ms_p50": float(np.median(t_del) * 1e3), "upsert_ms_p50": float(np.median(t_up) * 1e3),
-                            "max_ms": float(np.max(lat_mixed) * 1e3), "top5_ms": [float(x * 1e3) for x in np.sort(lat_mixed)[-5:]],
                             "delete_ms_mean": float(np.mean(t_del) * 1e3), "upsert_ms_mean": float(np.mean(t_up) * 1e3),
-                            "upsert_ms_all": [round(float(x * 1e3), 2) for x in t_up],
-                            "fallbacks": {"gemv": int(s1["fallback_gemv"] - s0["fallback_gemv"]),
-                                          "exhaustive": int(s1["fallback_exhaustive"] - s0["fallback_exhaustive"])},
                             "rows_moved_by_compaction": int(s1["rows_moved"] - s0["rows_moved"])},
-            "e2e": {"value": n_search / mixed_s, "unit": UNIT, "h2d_bytes_per_step": DIM * 4 + n_rows_written * DIM * 4 // n_search,
-                    "d2h_bytes_per_step": K * 24 + 4},
+            "fallbacks": {"gemv": int(s1["fallback_gemv"] - s0["fallback_gemv"]),
+                          "exhaustive": int(s1["fallback_exhaustive"] - s0["fallback_exhaustive"])},
             "gpu_launches": int(s1["kernel_launches"] - s0["kernel_launches"]),
-            "verify": {"new_rows_searchable_and_table_size_constant": ok}}
+            "h2d_bytes_per_step": DIM * 4 + n_rows_written * DIM * 4 // n_search, "d2h_bytes_per_step": K * 24 + 4,
+            "verify": {"new_rows_searchable_deleted_rows_gone_table_size_constant": ok}}
+
+
+def run_mixed(a):
+    import torch
+    import outline_rag_b200 as orx
+    torch.cuda.set_device(0)
+    ix = orx.Index(a.dtype, a.rows + 200_000, 0)
+    ix.use_torch_stream()
+    build_table(ix.upsert, 0, a.rows, 0, 1)
+    r = mixed_on(ix, a.rows, a.dtype, a.mixed_rounds)
+    line = {"metric": METRIC + "_mixed", "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": r["steps"], "warmup": 70,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if a.dtype == "fp32" else "bf16", "data": "synthetic", "config": r["config"],
+            "search_only": r["search_only"], "with_writer": r["with_writer"], "fallbacks": r["fallbacks"],
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d_bytes_per_step"],
+                    "d2h_bytes_per_step": r["d2h_bytes_per_step"]},
+            "gpu_launches": r["gpu_launches"], "verify": r["verify"]}
     print(json.dumps(line), flush=True)
+    ix.close()
 
 
 def main():
