@@ -167,9 +167,17 @@ void launch_merge_wait(int world, int rank, int nq, int k, const void *set_base,
                        int *out_counts, int *flags_any, int *flags_mine, int *redo, uint32_t *err_host,
                        const DoneArgs &done, cudaStream_t st) {
     if (nq <= 0) return;
-    merge_wait_kernel<<<nq, 256, 0, st>>>(world, rank, nq, k, static_cast<const char *>(set_base), slot_stride,
-                                          dist_off, counts_off, flags_off, arrival, arrival_stride_words, seq,
-                                          out_ids, out_dist, out_counts, flags_any, flags_mine, redo, err_host, done);
+    // Small batches: launched with the programmatic-serialization attribute, so the merge CTAs are resident and polling
+    // the arrival words while this rank's finalize still runs (they synchronise through the words and system fences, not
+    // through grid completion).  Safe only while the polling CTAs cannot crowd finalize's CTAs out of the SMs: nq <= 128.
+    if (nq <= 128)
+        launch_pdl(merge_wait_kernel, dim3(nq), dim3(256), 0, st, world, rank, nq, k, static_cast<const char *>(set_base),
+                   slot_stride, dist_off, counts_off, flags_off, arrival, arrival_stride_words, seq, out_ids, out_dist,
+                   out_counts, flags_any, flags_mine, redo, err_host, done);
+    else
+        merge_wait_kernel<<<nq, 256, 0, st>>>(world, rank, nq, k, static_cast<const char *>(set_base), slot_stride,
+                                              dist_off, counts_off, flags_off, arrival, arrival_stride_words, seq,
+                                              out_ids, out_dist, out_counts, flags_any, flags_mine, redo, err_host, done);
 }
 
 }  // namespace orx

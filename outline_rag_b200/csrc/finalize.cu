@@ -128,6 +128,7 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
         s_valid = 0;
     }
     pdl_wait();                         // the scan that filled `partial` has completed (no-op for a plain launch)
+    pdl_launch_dependents();            // a merge_wait launched behind this grid may take its SM now and start polling
 
     // 1. the query's top-K candidates by fast score.
     __shared__ uint64_t s_surv[FIN_SURV];
