@@ -68,6 +68,13 @@ def _is_cuda_tensor(x) -> bool:
     return torch is not None and isinstance(x, torch.Tensor) and x.is_cuda
 
 
+def _fence_producer(t) -> None:
+    """A multi-GPU index launches on its own per-device streams: work that torch still has in flight on the tensor's
+    current stream (the kernel that PRODUCES a query batch or a row block) must be finished before the library reads it.
+    (A single-GPU index shares torch's stream after `use_torch_stream()`, or the legacy default stream.)"""
+    torch.cuda.current_stream(t.device).synchronize()
+
+
 def _host_f32(x, what: str) -> np.ndarray:
     if torch is not None and isinstance(x, torch.Tensor):
         x = x.detach().cpu().numpy()
@@ -259,6 +266,8 @@ class Index:
             if vecs.dim() != 2 or vecs.dtype != torch.float32:
                 raise _lib.OrxValueError(_lib.ORX_ERR_DIM, "device vecs must be a float32 [n, dim] tensor")
             v = vecs.contiguous()
+            if len(self.devices) > 1:
+                _fence_producer(v)
             n, dim, ptr = v.shape[0], v.shape[1], v.data_ptr()
         else:
             v = _host_f32(vecs, "vecs")
@@ -303,6 +312,8 @@ class Index:
             if q.dtype != torch.float32:
                 raise _lib.OrxValueError(_lib.ORX_ERR_INVALID, "device queries must be float32")
             nq, dim = q.shape
+            if len(self.devices) > 1:
+                _fence_producer(q)
             if out is not None:
                 ids, dist, cnt = out
             else:
