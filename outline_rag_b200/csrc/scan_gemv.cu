@@ -21,6 +21,33 @@
 
 namespace orx {
 
+// per-CTA merge by counting, shared by both scan kernels: the 8 warp lists hold 8*K distinct keys (0 = empty); a key's rank
+// is the number of larger keys, ranks < K are the CTA's sorted top-K -> partial[0..K)
+template <int S>
+__device__ __forceinline__ void cta_merge_store(const WarpTopK<S> &top, uint64_t (&s_keys)[SCAN_WARPS][32 * S],
+                                                uint64_t *__restrict__ partial, int lane, int warp) {
+    constexpr int K = 32 * S;
+    top.store(s_keys[warp], lane);
+    __syncthreads();
+    const uint64_t *all = &s_keys[0][0];
+    constexpr int TOTAL = SCAN_WARPS * K;
+    int nonzero = 0;
+#pragma unroll
+    for (int h = 0; h < TOTAL / SCAN_THREADS; ++h) {
+        const uint64_t mine = all[threadIdx.x + h * SCAN_THREADS];
+        nonzero += (mine != 0ull);
+        if (mine == 0ull) continue;
+        int rank = 0;
+#pragma unroll 8
+        for (int i = 0; i < TOTAL; ++i) rank += (all[i] > mine);
+        if (rank < K) partial[rank] = mine;
+    }
+    int nnz = 0;
+#pragma unroll
+    for (int j = 1; j <= TOTAL / SCAN_THREADS; ++j) nnz += __syncthreads_count(nonzero >= j);
+    if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
+}
+
 template <typename T> struct RowsPerIter { static constexpr int value = sizeof(T) == 4 ? 2 : 4; };   // 8 KB per warp in flight
 
 template <typename T, int S>
@@ -69,27 +96,7 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
         }
     }
 
-    // per-CTA merge by counting: the 8 warp lists hold 8*K distinct keys (0 = empty); a key's rank
-    // is the number of larger keys, ranks < K are the CTA's sorted top-K.
-    top.store(s_keys[warp], lane);
-    __syncthreads();
-    const uint64_t *all = &s_keys[0][0];
-    constexpr int TOTAL = SCAN_WARPS * K;
-    int nonzero = 0;
-#pragma unroll
-    for (int h = 0; h < TOTAL / SCAN_THREADS; ++h) {
-        const uint64_t mine = all[threadIdx.x + h * SCAN_THREADS];
-        nonzero += (mine != 0ull);
-        if (mine == 0ull) continue;
-        int rank = 0;
-#pragma unroll 8
-        for (int i = 0; i < TOTAL; ++i) rank += (all[i] > mine);
-        if (rank < K) partial[rank] = mine;
-    }
-    int nnz = 0;                                     // total non-empty keys = sum_j #{threads holding >= j}
-#pragma unroll
-    for (int j = 1; j <= TOTAL / SCAN_THREADS; ++j) nnz += __syncthreads_count(nonzero >= j);
-    if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
+    cta_merge_store<S>(top, s_keys, partial, lane, warp);
 }
 
 // ------------------------------------------------------------------ filtered scan
@@ -99,33 +106,6 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
 // = 32 consecutive rows per warp; rows whose bit is clear are never loaded, so HBM traffic is
 // eligible_rows * row_bytes.  Scores come from the same instruction sequence as the unfiltered scan
 // (scan_common.cuh), so the same error bound and the same completeness proof apply.
-// (The per-CTA merge below restates the one inside scan_gemv_kernel, which is left textually as it was
-// measured: folding both into one helper changes that kernel's register allocation.)
-template <int S>
-__device__ __forceinline__ void cta_merge_store(const WarpTopK<S> &top, uint64_t (&s_keys)[SCAN_WARPS][32 * S],
-                                                uint64_t *__restrict__ partial, int lane, int warp) {
-    constexpr int K = 32 * S;
-    top.store(s_keys[warp], lane);
-    __syncthreads();
-    const uint64_t *all = &s_keys[0][0];
-    constexpr int TOTAL = SCAN_WARPS * K;
-    int nonzero = 0;
-#pragma unroll
-    for (int h = 0; h < TOTAL / SCAN_THREADS; ++h) {
-        const uint64_t mine = all[threadIdx.x + h * SCAN_THREADS];
-        nonzero += (mine != 0ull);
-        if (mine == 0ull) continue;
-        int rank = 0;
-#pragma unroll 8
-        for (int i = 0; i < TOTAL; ++i) rank += (all[i] > mine);
-        if (rank < K) partial[rank] = mine;
-    }
-    int nnz = 0;
-#pragma unroll
-    for (int j = 1; j <= TOTAL / SCAN_THREADS; ++j) nnz += __syncthreads_count(nonzero >= j);
-    if ((int)threadIdx.x < K && (int)threadIdx.x >= nnz) partial[threadIdx.x] = 0ull;
-}
-
 template <typename T, int S>
 __global__ void __launch_bounds__(SCAN_THREADS, 2)
 scan_gemv_filtered_kernel(const T *__restrict__ table, const float *__restrict__ scale, uint32_t n_rows,
