@@ -11,7 +11,9 @@ BASELINE.json's metric is quoted on; 41 GB, fits one B200).
 
 Output: ONE JSON line on rank 0.
   value      whole-job QPS over EXACTLY K steps, queries already in HBM, results left in HBM (CUDA events on the
-             launching stream, barrier + synchronize on both sides, max over ranks)
+             launching stream, barrier + synchronize on both sides, max over ranks), with TWO searches in flight
+             (orx_search_submit / orx_search_wait: the throughput mode of the engine); `closed_loop` repeats the same K
+             steps as a loop of dependent calls (each search complete before the next is issued)
   e2e        the same through the public host API on HOST buffers: per step the query batch goes host->device and
              ids / distances / counts come back device->host inside the timed region
   latency    closed-loop p50 / p99 over a separately timed run of >= 1 s (K may be too small for percentiles)
@@ -392,6 +394,31 @@ class Bench:
             self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
         return float(ms.item()), lat
 
+    def timed_pipelined(self, sh, batches, steps, warmup):
+        """EXACTLY `steps` searches with TWO in flight (`search_submit` / `search_wait`, device buffers): the host side
+        and the first kernels of query i+1 overlap finalize / exchange / merge / completion of query i -- the engine's
+        throughput mode.  Same bracketing as `timed` (barrier + synchronize on both sides, CUDA events, max over ranks)."""
+        torch = self.torch
+        n = len(batches)
+        for i in range(warmup):
+            sh.search(batches[i % n], K)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        prev = None
+        for i in range(steps):
+            t, _ = sh.search_submit(batches[(warmup + i) % n], K)
+            if prev is not None:
+                sh.search_wait(prev)
+            prev = t
+        sh.search_wait(prev)
+        e1.record()
+        self.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(ms, op=self.dist.ReduceOp.MAX)
+        return float(ms.item())
+
     # -------------------------------------------------------------- e2e at N > 1: ONE process drives all the GPUs
     def group_e2e(self, rows, dtype, B, steps, warmup, check_queries, check_ids, check_dist):
         """The call a user of the drop-in makes on a multi-GPU box: `Index(devices=[0..N-1])` (what
@@ -520,11 +547,19 @@ class Bench:
         from outline_rag_b200._lib import ORX_OPT_SCAN_TIMING
         sampler = ClockSampler(self.local).start() if self.rank == 0 else None
         if want_latency:
-            # (1) the headline region: EXACTLY `steps` steps, no instrumentation inside the library
+            # (1) the headline region: EXACTLY `steps` steps, no instrumentation inside the library, two searches in
+            #     flight (throughput); then the same `steps` steps as a closed loop of dependent calls (latency)
             ix.set_option(ORX_OPT_SCAN_TIMING, 0)
+            pipelined = self.world == 1 or sh.exchange == "p2p"
             l0 = ix.stats()
-            total_ms, lat = self.timed(step_device, steps, warmup)
-            l1 = ix.stats()
+            if pipelined:
+                total_ms = self.timed_pipelined(sh, dev_batches, steps, warmup)
+                l1 = ix.stats()
+                closed_ms, lat = self.timed(step_device, steps, warmup)
+            else:
+                total_ms, lat = self.timed(step_device, steps, warmup)
+                l1 = ix.stats()
+                closed_ms = total_ms
             # (2) the same loop again with a CUDA event pair recorded around every scan launch (on the stream the kernel
             #     runs on): the kernel's own duration for the roofline.  The two event records cost ~10 us per step, which
             #     is why they are not in region (1); this region's step time is reported beside the kernel time.
@@ -540,7 +575,8 @@ class Bench:
             l0 = s0 = ix.stats()
             total_ms, lat = self.timed(step_device, steps, warmup)
             l1 = s1 = ix.stats()
-            ev_ms = total_ms
+            ev_ms = closed_ms = total_ms
+            pipelined = False
             ix.set_option(ORX_OPT_SCAN_TIMING, 0)
         lat_run = None
         if want_latency:
@@ -606,7 +642,11 @@ class Bench:
             "roofline": roof, "clocks": clocks, "verify": verify,
             "fallbacks": {"gemv": int(s1["fallback_gemv"] - l0["fallback_gemv"]),
                           "exhaustive": int(s1["fallback_exhaustive"] - l0["fallback_exhaustive"])},
-            "run": {"rows_per_gpu": owned, "parallelism": f"row-shard x{self.world}", "exchange": sh.exchange},
+            "run": {"rows_per_gpu": owned, "parallelism": f"row-shard x{self.world}", "exchange": sh.exchange,
+                    "searches_in_flight": 2 if pipelined else 1},
+            "closed_loop": {"value": B * steps / (closed_ms * 1e-3), "unit": UNIT, "ms_per_step": closed_ms / steps,
+                            "steps": steps, "how": "the same steps as a loop of dependent calls: each search is complete "
+                                                   "before the next is issued (value: two searches in flight)"},
         }
         if lat_run is not None:
             res["latency"] = {"queries_per_step": B, "steps": int(lat_run.size), "seconds": float(lat_run.sum()),
@@ -693,7 +733,8 @@ def run_ours(a):
                 "warmup": head["warmup"], "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32" if a.dtype == "fp32" else "bf16", "data": "synthetic",
                 "config": head["config"], "run": dict(head["run"], table_build_s=round(build_s, 2)),
-                "p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "latency": head.get("latency"),
+                "p50_ms": head["p50_ms"], "p99_ms": head["p99_ms"], "closed_loop": head.get("closed_loop"),
+            "latency": head.get("latency"),
                 "e2e": group_e2e if group_e2e is not None else head.get("e2e"),
                 "gpu_launches": head["gpu_launches"], "roofline": head["roofline"], "clocks": head["clocks"],
                 "verify": head["verify"], "fallbacks": head["fallbacks"]}

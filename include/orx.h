@@ -126,6 +126,20 @@ int orx_contains(const orx_index *idx, orx_id id);
 int orx_search(orx_index *idx, const float *queries, int nq, int dim, int k,
                orx_id *out_ids, double *out_dist, int *out_counts);
 
+/* The same search in two halves, so that a caller can keep TWO searches in flight per index (the host side of the next
+ * query -- staging, launches -- and its first kernels overlap the tail of the previous one: finalize, exchange, merge,
+ * the completion hand-shake).  orx_search_submit launches the whole chain and returns at once with a ticket;
+ * orx_search_wait(ticket) blocks until that search is complete, settles whatever the fast path could not prove, and
+ * fills the output buffers given at submit (they and, for host queries, nothing else must stay valid until then;
+ * the queries are copied at submit).  At most two tickets may be outstanding; wait for them in submission order.
+ * orx_search == submit + wait.  orx_search_sharded_submit is the same for the collective row-sharded search (every
+ * rank submits and waits in the same order; its tickets are waited for with orx_search_wait too). */
+int orx_search_submit(orx_index *idx, const float *queries, int nq, int dim, int k,
+                      orx_id *out_ids, double *out_dist, int *out_counts, int *ticket);
+int orx_search_wait(orx_index *idx, int ticket);
+int orx_search_sharded_submit(orx_index *idx, const float *queries, int nq, int dim, int k,
+                              orx_id *out_ids, double *out_dist, int *out_counts, int *ticket);
+
 /* The same query restricted to a set of chunk ids -- the SQL with a WHERE clause, i.e. what the
  * upstream store's `filter=` argument compiles to after the metadata predicate has been resolved to
  * `langchain_id`s (e.g. `source_id = ANY(...)`, reference app/rag.py:216-224 shows that look-up).

@@ -88,6 +88,9 @@ SIGNATURES = {
     "orx_delete": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "orx_contains": (C.c_int, [_vp, OrxId]),
     "orx_search": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "orx_search_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(C.c_int)]),
+    "orx_search_wait": (C.c_int, [_vp, C.c_int]),
+    "orx_search_sharded_submit": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.POINTER(C.c_int)]),
     "orx_search_filtered": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _vp, C.c_uint64, _vp, _vp, _vp]),
     "orx_filter_create": (C.c_int, [_vp, _vp, C.c_uint64, C.POINTER(_vp)]),
     "orx_filter_destroy": (None, [_vp]),

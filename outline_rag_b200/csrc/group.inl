@@ -306,21 +306,21 @@ int group_search_chunk(Group *g, const float *queries, int nq, int k, orx_id *ou
     }
     {
         DeviceGuard dg(root->device);
-        CK(root->h_flags.ensure(nq));
-        CK(root->h_myflags.ensure(nq));
-        CK(root->h_redo.ensure(1));
+        CK(root->cur->h_flags.ensure(nq));
+        CK(root->cur->h_myflags.ensure(nq));
+        CK(root->cur->h_redo.ensure(1));
         if (!out_on_dev) {
-            CK(root->h_ids.ensure(nk));
-            CK(root->h_dist.ensure(nk));
-            CK(root->h_counts.ensure(nq));
+            CK(root->cur->h_ids.ensure(nk));
+            CK(root->cur->h_dist.ensure(nk));
+            CK(root->cur->h_counts.ensure(nq));
         }
         int rc0 = ensure_signalling(root);
         if (rc0 != ORX_OK) return rc0;
     }
-    const orx::ResultOut final_out{out_on_dev ? out_ids : root->h_ids.p, out_on_dev ? out_dist : root->h_dist.p,
-                                   out_on_dev ? out_counts : root->h_counts.p, root->h_flags.p};
-    *root->h_redo.p = 0;
-    root->h_done.p[1] = 0;
+    const orx::ResultOut final_out{out_on_dev ? out_ids : root->cur->h_ids.p, out_on_dev ? out_dist : root->cur->h_dist.p,
+                                   out_on_dev ? out_counts : root->cur->h_counts.p, root->cur->h_flags.p};
+    *root->cur->h_redo.p = 0;
+    root->cur->h_done.p[1] = 0;
     const uint32_t seq = ++g->seq;
     const uint32_t token = next_token(root);
     std::vector<int> paths(G, 1);
@@ -344,25 +344,25 @@ int group_search_chunk(Group *g, const float *queries, int nq, int k, orx_id *ou
         if (rc == ORX_OK) rc = rw;
     }
     if (rc != ORX_OK) return rc;
-    if (root->h_done.p[1]) return fail(ORX_ERR_CUDA, "multi-GPU search: a shard did not publish its candidates within 10 s");
+    if (root->cur->h_done.p[1]) return fail(ORX_ERR_CUDA, "multi-GPU search: a shard did not publish its candidates within 10 s");
     bool any_unproven = false;
     for (int j = 0; j < nq; ++j) {
-        const int f = root->h_flags.p[j];
+        const int f = root->cur->h_flags.p[j];
         if (f & 8) return fail(ORX_ERR_CUDA, "multi-GPU search: a shard failed (query %d)", j);
         if (f & 2) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
         any_unproven |= (f & 1) != 0;
     }
     if (!out_on_dev) {
-        memcpy(out_ids, root->h_ids.p, nk * sizeof(orx_id));
-        memcpy(out_dist, root->h_dist.p, nk * sizeof(double));
-        memcpy(out_counts, root->h_counts.p, nq * sizeof(int));
+        memcpy(out_ids, root->cur->h_ids.p, nk * sizeof(orx_id));
+        memcpy(out_dist, root->cur->h_dist.p, nk * sizeof(double));
+        memcpy(out_counts, root->cur->h_counts.p, nq * sizeof(int));
     }
     if (any_unproven) {
         std::vector<float> qh(ORX_DIM);
         std::vector<orx_id> ti(k);
         std::vector<double> td(k);
         for (int j = 0; j < nq; ++j) {
-            if (!(root->h_flags.p[j] & 1)) continue;
+            if (!(root->cur->h_flags.p[j] & 1)) continue;
             const float *qj = queries + (size_t)j * ORX_DIM;
             if (is_device_ptr(queries)) {
                 CK(cudaMemcpy(qh.data(), qj, ORX_DIM * sizeof(float), cudaMemcpyDeviceToHost));

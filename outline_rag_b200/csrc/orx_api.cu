@@ -155,6 +155,46 @@ struct Exchange {   // peer-memory exchange state of one rank (orx_shard_*) or o
 };
 
 
+struct SlotLayoutPod {      // layout of one rank's result block for (nq, k) -- see slot_layout()
+    size_t dist_off = 0, counts_off = 0, flags_off = 0, bytes = 0;
+};
+struct SearchSlot {         // everything ONE search in flight owns
+    DevBuf<float> q_dev, qhat;
+    DevBuf<__nv_bfloat16> qhat16;
+    DevBuf<orx::QueryPrep> prep;
+    DevBuf<uint64_t> partial;
+    DevBuf<double> blk;                 // scratch result block (empty shard / error block of the row-sharded search)
+    PinBuf<float> h_q;
+    PinBuf<orx::QueryPrep> h_prep;
+    PinBuf<orx_id> h_ids;
+    PinBuf<double> h_dist;
+    PinBuf<int> h_counts, h_flags, h_myflags, h_redo;
+    PinBuf<uint32_t> h_done;            // [0] completion word the last CTA of a search writes (host polls it), [1] error word
+    DevBuf<unsigned int> d_counters;    // [0] finalize CTAs, [1] merge CTAs of the search in flight (0 between searches)
+    std::vector<cudaEvent_t> scan_ev;   // pairs bracketing each scan launch of the search
+    size_t scan_ev_used = 0;
+    orx::UmmaPlan *umma = nullptr;
+    // the search in flight in this slot (orx_search_submit ... orx_search_wait)
+    struct Pending {
+        bool active = false, complete = false, sharded = false, out_on_dev = false;
+        int nq = 0, k = 0, path = 1;
+        orx_id *out_ids = nullptr;
+        double *out_dist = nullptr;
+        int *out_counts = nullptr;
+        const float *q_src = nullptr;
+        uint32_t token = 0, seq = 0, ticket = 0;
+        SlotLayoutPod L;
+        std::chrono::steady_clock::time_point t_begin;
+    } pend;
+    void release() {
+        q_dev.release(); qhat.release(); qhat16.release(); prep.release(); partial.release(); blk.release();
+        h_q.release(); h_prep.release(); h_ids.release(); h_dist.release(); h_counts.release(); h_flags.release();
+        h_myflags.release(); h_redo.release(); h_done.release(); d_counters.release();
+        for (auto &e : scan_ev) cudaEventDestroy(e);
+        scan_ev.clear();
+    }
+};
+
 struct orx_index {
     int device = 0;
     int dtype = ORX_DTYPE_F32;
@@ -175,18 +215,11 @@ struct orx_index {
     std::vector<orx_id> host_row_ids;
     std::unordered_map<orx_id, uint32_t, IdHash, IdEq> map;
 
-    // search scratch
-    DevBuf<float> q_dev, qhat;
-    DevBuf<__nv_bfloat16> qhat16;
-    DevBuf<orx::QueryPrep> prep;
-    DevBuf<uint64_t> partial;
-    PinBuf<float> h_q;
-    PinBuf<orx::QueryPrep> h_prep;
-    PinBuf<orx_id> h_ids;
-    PinBuf<double> h_dist;
-    PinBuf<int> h_counts, h_flags, h_myflags, h_redo;
-    PinBuf<uint32_t> h_done;            // [0] completion word the last CTA of a search writes (host polls it), [1] error word
-    DevBuf<unsigned int> d_counters;    // [0] finalize CTAs, [1] merge CTAs of the search in flight (0 between searches)
+    // search scratch: TWO complete sets, so that one search can be launched while the previous one is still in flight
+    // (orx_search_submit / orx_search_wait); `cur` = the set the search being submitted / completed works on
+    SearchSlot slot[2];
+    SearchSlot *cur = &slot[0];
+    uint32_t tickets = 0;               // searches submitted so far; ticket t lives in slot[t & 1]
     uint32_t token = 0;                 // last completion token handed out (never 0)
     bool scan_timing = true;            // ORX_OPT_SCAN_TIMING
     struct Exchange *xchg = nullptr;     // peer-memory exchange of the row-sharded search (orx_shard_*)
@@ -205,9 +238,6 @@ struct orx_index {
     PinBuf<uint32_t> h_u32a, h_u32b;
     PinBuf<int> h_flag;
 
-    std::vector<cudaEvent_t> scan_ev;   // pairs bracketing each scan launch of the current search
-    size_t scan_ev_used = 0;
-    orx::UmmaPlan *umma = nullptr;
     mutable std::mutex mu;
     orx_stats stats{};
 };
@@ -295,7 +325,8 @@ int grow_table(orx_index *ix, uint64_t need) {
     ix->n2 = n;
     ix->row_ids = r;
     ix->capacity = cap;
-    if (ix->umma) orx::umma_plan_invalidate(ix->umma);
+    for (SearchSlot &sl : ix->slot)
+        if (sl.umma) orx::umma_plan_invalidate(sl.umma);
     return ORX_OK;
 }
 
@@ -418,25 +449,25 @@ int upsert_locked(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t 
 // a fresh event from the per-search pool (pairs: before / after one scan launch)
 cudaEvent_t scan_event(orx_index *ix) {
     if (!ix->scan_timing) return nullptr;
-    if (ix->scan_ev_used == ix->scan_ev.size()) {
+    if (ix->cur->scan_ev_used == ix->cur->scan_ev.size()) {
         cudaEvent_t e = nullptr;
         if (cudaEventCreate(&e) != cudaSuccess) return nullptr;
-        ix->scan_ev.push_back(e);
+        ix->cur->scan_ev.push_back(e);
     }
-    return ix->scan_ev[ix->scan_ev_used++];
+    return ix->cur->scan_ev[ix->cur->scan_ev_used++];
 }
 void harvest_scan_events(orx_index *ix) {       // stream is synchronised
     float last = 0.f;
-    for (size_t i = 0; i + 1 < ix->scan_ev_used; i += 2) {
+    for (size_t i = 0; i + 1 < ix->cur->scan_ev_used; i += 2) {
         float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, ix->scan_ev[i], ix->scan_ev[i + 1]) == cudaSuccess) {
+        if (cudaEventElapsedTime(&ms, ix->cur->scan_ev[i], ix->cur->scan_ev[i + 1]) == cudaSuccess) {
             ix->stats.scan_ms_total += ms;
             ix->stats.scan_launches += 1;
             last += ms;
         }
     }
-    if (ix->scan_ev_used) ix->stats.last_scan_ms = last;
-    ix->scan_ev_used = 0;
+    if (ix->cur->scan_ev_used) ix->stats.last_scan_ms = last;
+    ix->cur->scan_ev_used = 0;
     cudaGetLastError();
 }
 
@@ -467,10 +498,10 @@ int exhaustive_query(orx_index *ix, const float *q_src, int qi, int k, double dk
         floor_f = nextafterf(floor_f, -INFINITY);     // conversion may have rounded up
     }
     CK(cudaMemsetAsync(ix->fb_count.p, 0, sizeof(uint32_t), ix->stream));
-    orx::launch_collect(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qi * ORX_DIM, floor_f,
+    orx::launch_collect(ix->dtype, ix->table, ix->scale, n_rows, ix->cur->qhat.p + (size_t)qi * ORX_DIM, floor_f,
                         all ? 1 : 0, ix->fb_list.p, ix->fb_count.p, ix->stream);
     orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)qi * ORX_DIM,
-                             ix->prep.p + qi, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, ix->stream);
+                             ix->cur->prep.p + qi, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, ix->stream);
     orx::launch_select_list(ix->row_ids, ix->fb_list.p, ix->fb_count.p, ix->fb_dist.p, k,
                             out.ids + (size_t)qi * k, out.dist + (size_t)qi * k, out.counts + qi, ix->stream);
     ix->stats.kernel_launches += 3;
@@ -487,14 +518,14 @@ int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const Se
     for (int s = 0; s < nq; s += GEMV_QCHUNK) {
         const int m = std::min(GEMV_QCHUNK, nq - s);
         const int qa = q0 + s;
-        CK(ix->partial.ensure((size_t)m * grid * 32 * slots));
+        CK(ix->cur->partial.ensure((size_t)m * grid * 32 * slots));
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         if (e0 && e1) CK(cudaEventRecord(e0, ix->stream));
-        orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->qhat.p + (size_t)qa * ORX_DIM, m,
-                              slots, ix->partial.p, grid, ix->stream);
+        orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->cur->qhat.p + (size_t)qa * ORX_DIM, m,
+                              slots, ix->cur->partial.p, grid, ix->stream);
         if (e0 && e1) CK(cudaEventRecord(e1, ix->stream));
         orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)qa * ORX_DIM,
-                             ix->prep.p + qa, ix->partial.p, grid, slots, m, k, n_rows, eps, ctx.out, qa, ctx.pub,
+                             ix->cur->prep.p + qa, ix->cur->partial.p, grid, slots, m, k, n_rows, eps, ctx.out, qa, ctx.pub,
                              ctx.done, ix->stream);
         ix->stats.kernel_launches += 2;
     }
@@ -512,37 +543,37 @@ int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_s
     // the tcgen05 scan reads query tiles of 128 rows (256 per CTA pair): keep the buffers padded (and the pad zeroed) so
     // its TMA never touches an out-of-range row (measured: mostly-out-of-range query boxes cost ~40 %)
     const size_t nq_pad = ((size_t)nq + 255) / 256 * 256;
-    CK(ix->qhat.ensure(nq_pad * ORX_DIM));
-    CK(ix->qhat16.ensure(nq_pad * ORX_DIM));
-    CK(ix->prep.ensure(nq));
+    CK(ix->cur->qhat.ensure(nq_pad * ORX_DIM));
+    CK(ix->cur->qhat16.ensure(nq_pad * ORX_DIM));
+    CK(ix->cur->prep.ensure(nq));
     if (nq_pad != (size_t)nq && nq > 1) {
-        CK(cudaMemsetAsync(ix->qhat.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(float), st));
-        CK(cudaMemsetAsync(ix->qhat16.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(__nv_bfloat16), st));
+        CK(cudaMemsetAsync(ix->cur->qhat.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(float), st));
+        CK(cudaMemsetAsync(ix->cur->qhat16.p + (size_t)nq * ORX_DIM, 0, (nq_pad - nq) * ORX_DIM * sizeof(__nv_bfloat16), st));
     }
     const int qdev = ptr_device(queries);
     if (qdev == ix->device) {
         *q_src = queries;
-        orx::launch_prep_queries(queries, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+        orx::launch_prep_queries(queries, nq, nullptr, ix->cur->qhat.p, ix->cur->qhat16.p, ix->cur->prep.p, st);
     } else if (qdev >= 0) {
         // the batch lives on ANOTHER GPU (a group's shards all receive the root's pointer): the prep kernel reads it
         // over NVLink once and leaves a local copy for the rescoring kernels
-        CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
-        *q_src = ix->q_dev.p;
-        orx::launch_prep_queries(queries, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+        CK(ix->cur->q_dev.ensure((size_t)nq * ORX_DIM));
+        *q_src = ix->cur->q_dev.p;
+        orx::launch_prep_queries(queries, nq, ix->cur->q_dev.p, ix->cur->qhat.p, ix->cur->qhat16.p, ix->cur->prep.p, st);
     } else {
-        CK(ix->q_dev.ensure((size_t)nq * ORX_DIM));
+        CK(ix->cur->q_dev.ensure((size_t)nq * ORX_DIM));
         const float *pinned = queries;
         if (!src_pinned) {
-            CK(ix->h_q.ensure((size_t)nq * ORX_DIM));
-            memcpy(ix->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
-            pinned = ix->h_q.p;
+            CK(ix->cur->h_q.ensure((size_t)nq * ORX_DIM));
+            memcpy(ix->cur->h_q.p, queries, (size_t)nq * ORX_DIM * sizeof(float));
+            pinned = ix->cur->h_q.p;
         }
-        *q_src = ix->q_dev.p;
+        *q_src = ix->cur->q_dev.p;
         if (nq <= ZERO_COPY_MAX_Q) {
-            orx::launch_prep_queries(pinned, nq, ix->q_dev.p, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+            orx::launch_prep_queries(pinned, nq, ix->cur->q_dev.p, ix->cur->qhat.p, ix->cur->qhat16.p, ix->cur->prep.p, st);
         } else {
-            CK(cudaMemcpyAsync(ix->q_dev.p, pinned, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
-            orx::launch_prep_queries(ix->q_dev.p, nq, nullptr, ix->qhat.p, ix->qhat16.p, ix->prep.p, st);
+            CK(cudaMemcpyAsync(ix->cur->q_dev.p, pinned, (size_t)nq * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
+            orx::launch_prep_queries(ix->cur->q_dev.p, nq, nullptr, ix->cur->qhat.p, ix->cur->qhat16.p, ix->cur->prep.p, st);
         }
     }
     ix->stats.kernel_launches += 1;
@@ -552,11 +583,11 @@ int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_s
 // ---- the scan + finalize of all nq queries (tcgen05 for batches, GEMV otherwise); *path = 1 / 2
 int scan_pass(orx_index *ix, const float *q_src, int nq, int k, const SearchCtx &ctx, int *path) {
     const uint32_t n_rows = (uint32_t)ix->n_live;
-    if (ix->umma && k <= 32 && orx::umma_should_use(ix->umma, nq, n_rows)) {
+    if (ix->cur->umma && k <= 32 && orx::umma_should_use(ix->cur->umma, nq, n_rows)) {
         *path = 2;
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
-        int rc = orx::umma_search(ix->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
-                                  q_src, ix->qhat.p, ix->qhat16.p, ix->prep.p, nq, k, ctx.out, ctx.pub, ctx.done,
+        int rc = orx::umma_search(ix->cur->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
+                                  q_src, ix->cur->qhat.p, ix->cur->qhat16.p, ix->cur->prep.p, nq, k, ctx.out, ctx.pub, ctx.done,
                                   ix->stream, &ix->stats.kernel_launches, e0, e1);
         if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
         return ORX_OK;
@@ -573,7 +604,7 @@ uint32_t next_token(orx_index *ix) {
     return ix->token;
 }
 int wait_done(orx_index *ix, uint32_t token) {
-    volatile uint32_t *w = ix->h_done.p;
+    volatile uint32_t *w = ix->cur->h_done.p;
     for (uint64_t it = 0;; ++it) {
         if (*w == token) return ORX_OK;
         if ((it & 0x3FFu) == 0x3FFu) {
@@ -590,14 +621,14 @@ int wait_done(orx_index *ix, uint32_t token) {
     }
 }
 int ensure_signalling(orx_index *ix) {
-    if (!ix->h_done.p) {
-        CK(ix->h_done.ensure(2));
-        ix->h_done.p[0] = 0;
-        ix->h_done.p[1] = 0;
+    if (!ix->cur->h_done.p) {
+        CK(ix->cur->h_done.ensure(2));
+        ix->cur->h_done.p[0] = 0;
+        ix->cur->h_done.p[1] = 0;
     }
-    if (!ix->d_counters.p) {
-        CK(ix->d_counters.ensure(2));
-        CK(cudaMemsetAsync(ix->d_counters.p, 0, ix->d_counters.n * sizeof(unsigned int), ix->stream));
+    if (!ix->cur->d_counters.p) {
+        CK(ix->cur->d_counters.ensure(2));
+        CK(cudaMemsetAsync(ix->cur->d_counters.p, 0, ix->cur->d_counters.n * sizeof(unsigned int), ix->stream));
     }
     return ORX_OK;
 }
@@ -646,40 +677,49 @@ int resolve_unproven(orx_index *ix, const float *q_src, int nq, int k, const orx
     return ORX_OK;
 }
 
-int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
-                  int *out_counts) {
-    const auto t_begin = std::chrono::steady_clock::now();
-    const bool out_on_dev = is_device_ptr(out_ids);        // (out_dist / out_counts are documented to be of the same kind)
+// ---- a search = submit (launch the whole chain on the slot `ix->cur`, no waiting) + wait (poll the completion word,
+//      settle unproven queries, hand the results over).  orx_search is the two back to back; orx_search_submit /
+//      orx_search_wait let a caller keep two searches in flight.
+int search_submit_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
+                         int *out_counts) {
+    SearchSlot::Pending &pd = ix->cur->pend;
+    pd = SearchSlot::Pending{};
+    pd.t_begin = std::chrono::steady_clock::now();
+    pd.out_on_dev = is_device_ptr(out_ids);        // (out_dist / out_counts are documented to be of the same kind)
+    pd.nq = nq;
+    pd.k = k;
+    pd.out_ids = out_ids;
+    pd.out_dist = out_dist;
+    pd.out_counts = out_counts;
+    const bool out_on_dev = pd.out_on_dev;
     cudaStream_t st = ix->stream;
     const size_t nk = (size_t)nq * k;
-    ix->scan_ev_used = 0;
+    ix->cur->scan_ev_used = 0;
 
-    CK(ix->h_flags.ensure(nq));
+    CK(ix->cur->h_flags.ensure(nq));
     if (!out_on_dev) {
-        CK(ix->h_ids.ensure(nk));
-        CK(ix->h_dist.ensure(nk));
-        CK(ix->h_counts.ensure(nq));
+        CK(ix->cur->h_ids.ensure(nk));
+        CK(ix->cur->h_dist.ensure(nk));
+        CK(ix->cur->h_counts.ensure(nq));
     }
     // host-side results are written by the kernels straight into mapped pinned memory
-    int *flags = ix->h_flags.p;
-    const orx::ResultOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                             out_on_dev ? out_counts : ix->h_counts.p, flags};
+    int *flags = ix->cur->h_flags.p;
+    const orx::ResultOut out{out_on_dev ? out_ids : ix->cur->h_ids.p, out_on_dev ? out_dist : ix->cur->h_dist.p,
+                             out_on_dev ? out_counts : ix->cur->h_counts.p, flags};
     int rc = ensure_signalling(ix);
     if (rc != ORX_OK) return rc;
 
-    const float *q_src = nullptr;
-    rc = stage_queries(ix, queries, nq, &q_src);
+    rc = stage_queries(ix, queries, nq, &pd.q_src);
     if (rc != ORX_OK) return rc;
 
     const uint32_t n_rows = (uint32_t)ix->n_live;
-    int path = 1;
     if (n_rows == 0) {
-        // nothing to scan: only the pgvector input check matters
-        CK(ix->h_prep.ensure(nq));
-        CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
+        // nothing to scan: only the pgvector input check matters (settled here; the wait has nothing left to do)
+        CK(ix->cur->h_prep.ensure(nq));
+        CK(cudaMemcpyAsync(ix->cur->h_prep.p, ix->cur->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         for (int j = 0; j < nq; ++j)
-            if (ix->h_prep.p[j].nonfinite)
+            if (ix->cur->h_prep.p[j].nonfinite)
                 return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
         if (out_on_dev) {
             CK(cudaMemsetAsync(out_ids, 0, nk * sizeof(orx_id), st));
@@ -691,45 +731,80 @@ int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *ou
             memset(out_dist, 0xFF, nk * sizeof(double));
             memset(out_counts, 0, nq * sizeof(int));
         }
-        ix->stats.searches += 1;
-        ix->stats.queries += nq;
+        pd.active = true;
+        pd.complete = true;
         return ORX_OK;
     }
     SearchCtx ctx{};
     ctx.out = out;
-    const uint32_t token = next_token(ix);
-    ctx.done = orx::DoneArgs{ix->d_counters.p, (unsigned int)nq, ix->h_done.p, token};
-    rc = scan_pass(ix, q_src, nq, k, ctx, &path);
+    pd.token = next_token(ix);
+    ctx.done = orx::DoneArgs{ix->cur->d_counters.p, (unsigned int)nq, ix->cur->h_done.p, pd.token};
+    rc = scan_pass(ix, pd.q_src, nq, k, ctx, &pd.path);
     if (rc != ORX_OK) {
         cudaStreamSynchronize(st);          // part of the chain may be in flight: drain it, forget its count
-        cudaMemsetAsync(ix->d_counters.p, 0, 2 * sizeof(unsigned int), st);
+        cudaMemsetAsync(ix->cur->d_counters.p, 0, 2 * sizeof(unsigned int), st);
         cudaGetLastError();
         return rc;
     }
-    rc = wait_done(ix, token);              // the last finalize CTA wrote the completion word; flags are on the host
-    if (rc != ORX_OK) return rc;
+    pd.active = true;
+    return ORX_OK;
+}
 
-    bool any_unproven = false;
-    for (int j = 0; j < nq; ++j) {
-        if (flags[j] & 2) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
-        any_unproven |= (flags[j] & 1) != 0;
-    }
-    if (any_unproven) {
-        rc = resolve_unproven(ix, q_src, nq, k, out, flags, path, /*host_readable=*/!out_on_dev);
+int search_wait_locked(orx_index *ix) {
+    SearchSlot::Pending &pd = ix->cur->pend;
+    if (!pd.active) return fail(ORX_ERR_INVALID, "no search in flight under this ticket");
+    pd.active = false;
+    const int nq = pd.nq, k = pd.k;
+    if (!pd.complete) {
+        const size_t nk = (size_t)nq * k;
+        int *flags = ix->cur->h_flags.p;
+        const orx::ResultOut out{pd.out_on_dev ? pd.out_ids : ix->cur->h_ids.p, pd.out_on_dev ? pd.out_dist : ix->cur->h_dist.p,
+                                 pd.out_on_dev ? pd.out_counts : ix->cur->h_counts.p, flags};
+        int rc = wait_done(ix, pd.token);       // the last finalize CTA wrote the completion word; flags are on the host
         if (rc != ORX_OK) return rc;
+        bool any_unproven = false;
+        for (int j = 0; j < nq; ++j) {
+            if (flags[j] & 2) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
+            any_unproven |= (flags[j] & 1) != 0;
+        }
+        if (any_unproven) {
+            rc = resolve_unproven(ix, pd.q_src, nq, k, out, flags, pd.path, /*host_readable=*/!pd.out_on_dev);
+            if (rc != ORX_OK) return rc;
+        }
+        if (!pd.out_on_dev) {
+            memcpy(pd.out_ids, ix->cur->h_ids.p, nk * sizeof(orx_id));
+            memcpy(pd.out_dist, ix->cur->h_dist.p, nk * sizeof(double));
+            memcpy(pd.out_counts, ix->cur->h_counts.p, nq * sizeof(int));
+        }
+        harvest_scan_events(ix);
+        ix->stats.last_path = pd.path;
     }
-    if (!out_on_dev) {
-        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
-        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
-        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
-    }
-    harvest_scan_events(ix);
     ix->stats.last_search_ms =
-        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    ix->stats.last_path = path;
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - pd.t_begin).count();
     ix->stats.searches += 1;
     ix->stats.queries += nq;
     return ORX_OK;
+}
+
+// the slot of a new search: slots alternate with the ticket number; at most two searches are in flight
+int claim_slot(orx_index *ix, int *ticket) {
+    SearchSlot *sl = &ix->slot[ix->tickets & 1u];
+    if (sl->pend.active)
+        return fail(ORX_ERR_INVALID, "two searches are in flight already: wait for ticket %u first", ix->tickets - 2u);
+    ix->cur = sl;
+    if (ticket) *ticket = (int)(ix->tickets & 0x7FFFFFFFu);
+    return ORX_OK;
+}
+bool any_in_flight(const orx_index *ix) { return ix->slot[0].pend.active || ix->slot[1].pend.active; }
+
+int search_locked(orx_index *ix, const float *queries, int nq, int k, orx_id *out_ids, double *out_dist,
+                  int *out_counts) {
+    int rc = claim_slot(ix, nullptr);
+    if (rc != ORX_OK) return rc;
+    rc = search_submit_locked(ix, queries, nq, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK) return rc;
+    ix->tickets += 1;
+    return search_wait_locked(ix);
 }
 
 
@@ -798,21 +873,21 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
     const float *q_src = nullptr;
     int rc = stage_queries(ix, queries, nq, &q_src);
     if (rc != ORX_OK) return rc;
-    CK(ix->h_prep.ensure(nq));
-    CK(cudaMemcpyAsync(ix->h_prep.p, ix->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
+    CK(ix->cur->h_prep.ensure(nq));
+    CK(cudaMemcpyAsync(ix->cur->h_prep.p, ix->cur->prep.p, nq * sizeof(orx::QueryPrep), cudaMemcpyDeviceToHost, st));
     if (!out_on_dev) {
-        CK(ix->h_ids.ensure(nk));
-        CK(ix->h_dist.ensure(nk));
-        CK(ix->h_counts.ensure(nq));
+        CK(ix->cur->h_ids.ensure(nk));
+        CK(ix->cur->h_dist.ensure(nk));
+        CK(ix->cur->h_counts.ensure(nq));
     }
-    CK(ix->h_flags.ensure(nq));
-    const orx::ResultOut out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                             out_on_dev ? out_counts : ix->h_counts.p, ix->h_flags.p};
+    CK(ix->cur->h_flags.ensure(nq));
+    const orx::ResultOut out{out_on_dev ? out_ids : ix->cur->h_ids.p, out_on_dev ? out_dist : ix->cur->h_dist.p,
+                             out_on_dev ? out_counts : ix->cur->h_counts.p, ix->cur->h_flags.p};
     CK(ix->fb_dist.ensure(std::max<size_t>(m, 1)));
     // exact by construction: every eligible row is rescored canonically and the k best are selected
     auto list_query = [&](int j) {
         if (m)
-            orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)j * ORX_DIM, ix->prep.p + j,
+            orx::launch_rescore_list(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)j * ORX_DIM, ix->cur->prep.p + j,
                                      f.list, f.count, ix->fb_dist.p, st);
         orx::launch_select_list(ix->row_ids, f.list, f.count, ix->fb_dist.p, k, out.ids + (size_t)j * k,
                                 out.dist + (size_t)j * k, out.counts + j, st);
@@ -826,18 +901,18 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
         const uint32_t n_rows = (uint32_t)ix->n_live;
         const int grid = orx::scan_gemv_grid(ix->device, n_rows);
         const double eps = ix->dtype == ORX_DTYPE_F32 ? orx::EPS_GEMV_F32 : orx::EPS_GEMV_BF16;
-        ix->scan_ev_used = 0;
+        ix->cur->scan_ev_used = 0;
         for (int s0 = 0; s0 < nq; s0 += GEMV_QCHUNK) {
             const int mq = std::min(GEMV_QCHUNK, nq - s0);
-            CK(ix->partial.ensure((size_t)mq * grid * 32 * slots));
+            CK(ix->cur->partial.ensure((size_t)mq * grid * 32 * slots));
             cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
             if (e0 && e1) CK(cudaEventRecord(e0, st));
             orx::launch_scan_gemv_filtered(ix->dtype, ix->table, ix->scale, n_rows, f.bits,
-                                           ix->qhat.p + (size_t)s0 * ORX_DIM, mq, slots, ix->partial.p, grid, st);
+                                           ix->cur->qhat.p + (size_t)s0 * ORX_DIM, mq, slots, ix->cur->partial.p, grid, st);
             if (e0 && e1) CK(cudaEventRecord(e1, st));
             // n_rows argument = the eligible count: "every eligible row is a candidate" when it fits the list
-            orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)s0 * ORX_DIM, ix->prep.p + s0,
-                                 ix->partial.p, grid, slots, mq, k, m, eps, out, s0, orx::PublishArgs{}, orx::DoneArgs{}, st);
+            orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)s0 * ORX_DIM, ix->cur->prep.p + s0,
+                                 ix->cur->partial.p, grid, slots, mq, k, m, eps, out, s0, orx::PublishArgs{}, orx::DoneArgs{}, st);
             ix->stats.kernel_launches += 2;
         }
         CK(cudaStreamSynchronize(st));
@@ -845,7 +920,7 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
         harvest_scan_events(ix);
         ix->stats.last_path = 1;
         for (int j = 0; j < nq; ++j) {
-            if (!(ix->h_flags.p[j] & 1) || (ix->h_flags.p[j] & 2)) continue;
+            if (!(ix->cur->h_flags.p[j] & 1) || (ix->cur->h_flags.p[j] & 2)) continue;
             ix->stats.fallback_exhaustive += 1;
             list_query(j);
         }
@@ -856,12 +931,12 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     for (int j = 0; j < nq; ++j)
-        if (ix->h_prep.p[j].nonfinite)
+        if (ix->cur->h_prep.p[j].nonfinite)
             return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
     if (!out_on_dev) {
-        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
-        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
-        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
+        memcpy(out_ids, ix->cur->h_ids.p, nk * sizeof(orx_id));
+        memcpy(out_dist, ix->cur->h_dist.p, nk * sizeof(double));
+        memcpy(out_counts, ix->cur->h_counts.p, nq * sizeof(int));
     }
     ix->stats.searches += 1;
     ix->stats.queries += nq;
@@ -888,8 +963,8 @@ int launch_shard_merge(orx_index *ix, Exchange *x, int nq, int k, const orx::Res
     const uint32_t *arrival = reinterpret_cast<const uint32_t *>(x->base + x->flags_off + (size_t)set * x->world * XFLAG_STRIDE);
     orx::launch_merge_wait(x->world, x->rank, nq, k, x->base + (size_t)set * x->set_bytes, x->slot_bytes, L.dist_off,
                            L.counts_off, L.flags_off, arrival, (int)(XFLAG_STRIDE / 4), seq, final_out.ids,
-                           final_out.dist, final_out.counts, ix->h_flags.p, ix->h_myflags.p, ix->h_redo.p,
-                           ix->h_done.p + 1, orx::DoneArgs{ix->d_counters.p + 1, (unsigned int)nq, ix->h_done.p, token},
+                           final_out.dist, final_out.counts, ix->cur->h_flags.p, ix->cur->h_myflags.p, ix->cur->h_redo.p,
+                           ix->cur->h_done.p + 1, orx::DoneArgs{ix->cur->d_counters.p + 1, (unsigned int)nq, ix->cur->h_done.p, token},
                            ix->stream);
     ix->stats.kernel_launches += 1;
     CK(cudaGetLastError());
@@ -911,17 +986,17 @@ int launch_shard_publish(orx_index *ix, Exchange *x, const SlotLayout &L, uint32
 int shard_round1(orx_index *ix, Exchange *x, const float *queries, bool src_pinned, int nq, int k, const SlotLayout &L,
                  uint32_t seq, const float **q_src, int *path) {
     cudaStream_t st = ix->stream;
-    ix->scan_ev_used = 0;
+    ix->cur->scan_ev_used = 0;
     const int set = seq & 1;
     int rc = ensure_signalling(ix);
     if (rc == ORX_OK) rc = stage_queries(ix, queries, nq, q_src, src_pinned);
     if (rc == ORX_OK) {
         if (ix->n_live == 0) {
             // an empty shard contributes nothing (its peers may still hold rows); flags carry the query check
-            CK(ix->fb_dist.ensure((L.bytes + 7) / 8));          // scratch block: the shard may own no local slot
-            char *blk = reinterpret_cast<char *>(ix->fb_dist.p);
+            CK(ix->cur->blk.ensure((L.bytes + 7) / 8));         // scratch block: the shard may own no local slot
+            char *blk = reinterpret_cast<char *>(ix->cur->blk.p);
             cudaMemsetAsync(blk, 0, L.bytes, st);
-            orx::launch_flags_from_prep(ix->prep.p, nq, reinterpret_cast<int *>(blk + L.flags_off), st);
+            orx::launch_flags_from_prep(ix->cur->prep.p, nq, reinterpret_cast<int *>(blk + L.flags_off), st);
             orx::launch_publish(blk, x->d_peer_slot[set], x->d_peer_flag[set], x->n_targets, L.bytes, seq, st);
             ix->stats.kernel_launches += 2;
             if (cudaGetLastError() != cudaSuccess) rc = fail(ORX_ERR_CUDA, "publishing an empty shard's block failed");
@@ -929,16 +1004,16 @@ int shard_round1(orx_index *ix, Exchange *x, const float *queries, bool src_pinn
             SearchCtx ctx{};
             ctx.pub = orx::PublishArgs{reinterpret_cast<char *const *>(x->d_peer_slot[set]), x->d_peer_flag[set],
                                        x->n_targets, seq, L.dist_off, L.counts_off, L.flags_off};
-            ctx.done = orx::DoneArgs{ix->d_counters.p, (unsigned int)nq, nullptr, 0u};
+            ctx.done = orx::DoneArgs{ix->cur->d_counters.p, (unsigned int)nq, nullptr, 0u};
             rc = scan_pass(ix, *q_src, nq, k, ctx, path);
         }
     }
     if (rc != ORX_OK) {
         const std::string why = g_err;
         cudaStreamSynchronize(st);
-        if (ix->d_counters.p) cudaMemsetAsync(ix->d_counters.p, 0, 2 * sizeof(unsigned int), st);
-        if (ix->fb_dist.ensure((L.bytes + 7) / 8) == cudaSuccess) {
-            char *blk = reinterpret_cast<char *>(ix->fb_dist.p);
+        if (ix->cur->d_counters.p) cudaMemsetAsync(ix->cur->d_counters.p, 0, 2 * sizeof(unsigned int), st);
+        if (ix->cur->blk.ensure((L.bytes + 7) / 8) == cudaSuccess) {
+            char *blk = reinterpret_cast<char *>(ix->cur->blk.p);
             cudaMemsetAsync(blk, 0, L.bytes, st);
             orx::launch_fill_flags(reinterpret_cast<int *>(blk + L.flags_off), nq, 8, st);
             orx::launch_publish(blk, x->d_peer_slot[set], x->d_peer_flag[set], x->n_targets, L.bytes, seq, st);
@@ -950,64 +1025,89 @@ int shard_round1(orx_index *ix, Exchange *x, const float *queries, bool src_pinn
     return rc;
 }
 
-int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int nq, int k, orx_id *out_ids,
+int sharded_submit_locked(orx_index *ix, Exchange *x, const float *queries, int nq, int k, orx_id *out_ids,
                           double *out_dist, int *out_counts) {
-    const auto t_begin = std::chrono::steady_clock::now();
-    const bool out_on_dev = is_device_ptr(out_ids);
+    SearchSlot::Pending &pd = ix->cur->pend;
+    pd = SearchSlot::Pending{};
+    pd.t_begin = std::chrono::steady_clock::now();
+    pd.sharded = true;
+    pd.nq = nq;
+    pd.k = k;
+    pd.out_ids = out_ids;
+    pd.out_dist = out_dist;
+    pd.out_counts = out_counts;
+    const bool out_on_dev = pd.out_on_dev = is_device_ptr(out_ids);
     if (out_on_dev != is_device_ptr(out_dist) || out_on_dev != is_device_ptr(out_counts))
         return fail(ORX_ERR_INVALID, "out_ids, out_dist and out_counts must all be host or all be device");
-    cudaStream_t st = ix->stream;
     const size_t nk = (size_t)nq * k;
     const SlotLayout L = slot_layout(nq, k);
     if (L.bytes > x->slot_bytes) return fail(ORX_ERR_INVALID, "sharded search limited to %d queries per call", XQ_MAX);
+    pd.L = SlotLayoutPod{L.dist_off, L.counts_off, L.flags_off, L.bytes};
 
-    CK(ix->h_flags.ensure(nq));
-    CK(ix->h_myflags.ensure(nq));
-    CK(ix->h_redo.ensure(1));
+    CK(ix->cur->h_flags.ensure(nq));
+    CK(ix->cur->h_myflags.ensure(nq));
+    CK(ix->cur->h_redo.ensure(1));
     if (!out_on_dev) {
-        CK(ix->h_ids.ensure(nk));
-        CK(ix->h_dist.ensure(nk));
-        CK(ix->h_counts.ensure(nq));
+        CK(ix->cur->h_ids.ensure(nk));
+        CK(ix->cur->h_dist.ensure(nk));
+        CK(ix->cur->h_counts.ensure(nq));
     }
     int rc = ensure_signalling(ix);
     if (rc != ORX_OK) return rc;
-    const orx::ResultOut final_out{out_on_dev ? out_ids : ix->h_ids.p, out_on_dev ? out_dist : ix->h_dist.p,
-                                   out_on_dev ? out_counts : ix->h_counts.p, ix->h_flags.p};
-    *ix->h_redo.p = 0;
-    ix->h_done.p[1] = 0;
+    const orx::ResultOut final_out{out_on_dev ? out_ids : ix->cur->h_ids.p, out_on_dev ? out_dist : ix->cur->h_dist.p,
+                                   out_on_dev ? out_counts : ix->cur->h_counts.p, ix->cur->h_flags.p};
+    *ix->cur->h_redo.p = 0;
+    ix->cur->h_done.p[1] = 0;
 
     // ---- round 1: scan, finalize pushes my block into every rank's gather buffer, merge what arrives
-    const uint32_t seq = ++x->seq;
-    char *slot = x->base + (size_t)(seq & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;      // my block, local copy
-    const float *q_src = nullptr;
-    int path = 1;
-    rc = shard_round1(ix, x, queries, false, nq, k, L, seq, &q_src, &path);
+    pd.seq = ++x->seq;
+    rc = shard_round1(ix, x, queries, false, nq, k, L, pd.seq, &pd.q_src, &pd.path);
     if (rc != ORX_OK) return rc;
-    uint32_t token = next_token(ix);
-    rc = launch_shard_merge(ix, x, nq, k, final_out, L, seq, token);
+    pd.token = next_token(ix);
+    rc = launch_shard_merge(ix, x, nq, k, final_out, L, pd.seq, pd.token);
     if (rc != ORX_OK) return rc;
-    rc = wait_done(ix, token);
+    pd.active = true;
+    return ORX_OK;
+}
+
+int sharded_wait_locked(orx_index *ix, Exchange *x) {
+    SearchSlot::Pending &pd = ix->cur->pend;
+    if (!pd.active || !pd.sharded) return fail(ORX_ERR_INVALID, "no sharded search in flight under this ticket");
+    pd.active = false;
+    cudaStream_t st = ix->stream;
+    const int nq = pd.nq, k = pd.k;
+    const size_t nk = (size_t)nq * k;
+    const bool out_on_dev = pd.out_on_dev;
+    SlotLayout L;
+    L.dist_off = pd.L.dist_off; L.counts_off = pd.L.counts_off; L.flags_off = pd.L.flags_off; L.bytes = pd.L.bytes;
+    const orx::ResultOut final_out{out_on_dev ? pd.out_ids : ix->cur->h_ids.p, out_on_dev ? pd.out_dist : ix->cur->h_dist.p,
+                                   out_on_dev ? pd.out_counts : ix->cur->h_counts.p, ix->cur->h_flags.p};
+    char *slot = x->base + (size_t)(pd.seq & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;      // my block, local copy
+    int rc = wait_done(ix, pd.token);
     if (rc != ORX_OK) return rc;
-    if (ix->h_done.p[1]) return fail(ORX_ERR_CUDA, "sharded search: a peer rank did not publish its candidates within 10 s");
+    if (ix->cur->h_done.p[1]) return fail(ORX_ERR_CUDA, "sharded search: a peer rank did not publish its candidates within 10 s");
 
     for (int j = 0; j < nq; ++j) {
-        if (ix->h_flags.p[j] & 8) return fail(ORX_ERR_CUDA, "sharded search: a peer rank failed (query %d)", j);
-        if (ix->h_flags.p[j] & 2)
+        if (ix->cur->h_flags.p[j] & 8) return fail(ORX_ERR_CUDA, "sharded search: a peer rank failed (query %d)", j);
+        if (ix->cur->h_flags.p[j] & 2)
             return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector (query %d)", j);
     }
-    if (*ix->h_redo.p) {
+    if (*ix->cur->h_redo.p) {
         // ---- round 2 (every rank sees the same redo word): ranks with unproven queries re-answer them
-        //      exactly, everybody republishes and merges again under the next sequence number.
+        //      exactly, everybody republishes and merges again under the next sequence number.  (With another search in
+        //      flight that number selects the same buffer set as round 1 did; it is free again by then: this round is
+        //      stream-ordered behind the other search's merge, which needed every peer's publish, which every peer
+        //      issued after finishing ITS merge of round 1.)
         const uint32_t seq2 = ++x->seq;
         char *slot2 = x->base + (size_t)(seq2 & 1) * x->set_bytes + (size_t)x->rank * x->slot_bytes;
-        CK(cudaMemcpyAsync(slot2, slot, L.bytes, cudaMemcpyDeviceToDevice, st));
+        if (slot2 != slot) CK(cudaMemcpyAsync(slot2, slot, L.bytes, cudaMemcpyDeviceToDevice, st));
         const orx::ResultOut mine2{reinterpret_cast<orx_id *>(slot2), reinterpret_cast<double *>(slot2 + L.dist_off),
                                    reinterpret_cast<int *>(slot2 + L.counts_off), reinterpret_cast<int *>(slot2 + L.flags_off)};
         bool mine_unproven = false;
-        for (int j = 0; j < nq; ++j) mine_unproven |= (ix->h_myflags.p[j] & 1) != 0;
+        for (int j = 0; j < nq; ++j) mine_unproven |= (ix->cur->h_myflags.p[j] & 1) != 0;
         rc = ORX_OK;
         if (mine_unproven && ix->n_live > 0)
-            rc = resolve_unproven(ix, q_src, nq, k, mine2, ix->h_myflags.p, path, /*host_readable=*/false);
+            rc = resolve_unproven(ix, pd.q_src, nq, k, mine2, ix->cur->h_myflags.p, pd.path, /*host_readable=*/false);
         if (rc != ORX_OK) {
             const std::string why = g_err;
             orx::launch_fill_flags(mine2.flags, nq, 8, st);
@@ -1017,31 +1117,41 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
             g_err = why;
             return rc;
         }
-        *ix->h_redo.p = 0;
+        *ix->cur->h_redo.p = 0;
         rc = launch_shard_publish(ix, x, L, seq2);
         if (rc != ORX_OK) return rc;
-        token = next_token(ix);
+        const uint32_t token = next_token(ix);
         rc = launch_shard_merge(ix, x, nq, k, final_out, L, seq2, token);
         if (rc != ORX_OK) return rc;
         rc = wait_done(ix, token);
         if (rc != ORX_OK) return rc;
-        if (ix->h_done.p[1]) return fail(ORX_ERR_CUDA, "sharded search: a peer rank did not publish its candidates within 10 s");
+        if (ix->cur->h_done.p[1]) return fail(ORX_ERR_CUDA, "sharded search: a peer rank did not publish its candidates within 10 s");
         for (int j = 0; j < nq; ++j)
-            if (ix->h_flags.p[j] & 8) return fail(ORX_ERR_CUDA, "sharded search: a peer rank failed (query %d)", j);
-        if (*ix->h_redo.p) return fail(ORX_ERR_CUDA, "sharded search: a rank could not prove its candidates");
+            if (ix->cur->h_flags.p[j] & 8) return fail(ORX_ERR_CUDA, "sharded search: a peer rank failed (query %d)", j);
+        if (*ix->cur->h_redo.p) return fail(ORX_ERR_CUDA, "sharded search: a rank could not prove its candidates");
     }
     if (!out_on_dev) {
-        memcpy(out_ids, ix->h_ids.p, nk * sizeof(orx_id));
-        memcpy(out_dist, ix->h_dist.p, nk * sizeof(double));
-        memcpy(out_counts, ix->h_counts.p, nq * sizeof(int));
+        memcpy(pd.out_ids, ix->cur->h_ids.p, nk * sizeof(orx_id));
+        memcpy(pd.out_dist, ix->cur->h_dist.p, nk * sizeof(double));
+        memcpy(pd.out_counts, ix->cur->h_counts.p, nq * sizeof(int));
     }
     harvest_scan_events(ix);
     ix->stats.last_search_ms =
-        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
-    ix->stats.last_path = path;
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - pd.t_begin).count();
+    ix->stats.last_path = pd.path;
     ix->stats.searches += 1;
     ix->stats.queries += nq;
     return ORX_OK;
+}
+
+int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int nq, int k, orx_id *out_ids,
+                          double *out_dist, int *out_counts) {
+    int rc = claim_slot(ix, nullptr);
+    if (rc != ORX_OK) return rc;
+    rc = sharded_submit_locked(ix, x, queries, nq, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK) return rc;
+    ix->tickets += 1;
+    return sharded_wait_locked(ix, x);
 }
 
 #include "group.inl"
@@ -1119,7 +1229,8 @@ int orx_create(orx_index **out, int dim, int dtype, uint64_t capacity_rows, int 
         orx_destroy(ix);
         return rc;
     }
-    ix->umma = orx::umma_plan_create(device);
+    ix->slot[0].umma = orx::umma_plan_create(device);
+    ix->slot[1].umma = orx::umma_plan_create(device);
     ix->host_row_ids.reserve(cap);
     ix->map.reserve(cap);
     *out = ix;
@@ -1148,19 +1259,18 @@ void orx_destroy(orx_index *ix) {
     }
     DeviceGuard g(ix->device);
     cudaDeviceSynchronize();
-    if (ix->umma) orx::umma_plan_destroy(ix->umma);
+    for (SearchSlot &sl : ix->slot) {
+        if (sl.umma) orx::umma_plan_destroy(sl.umma);
+        sl.release();
+    }
     cudaFree(ix->table);
     cudaFree(ix->scale);
     cudaFree(ix->n2);
     cudaFree(ix->row_ids);
-    ix->q_dev.release(); ix->qhat.release(); ix->qhat16.release(); ix->prep.release(); ix->partial.release();
-    ix->h_q.release(); ix->h_prep.release(); ix->h_ids.release(); ix->h_dist.release();
-    ix->h_counts.release(); ix->h_flags.release();
     ix->fb_list.release(); ix->fb_count.release(); ix->fb_dist.release();
     ix->allow_bits.release(); ix->h_allow_bits.release();
     ix->stage.release(); ix->d_src_idx.release(); ix->d_dst_row.release(); ix->d_ids.release();
     ix->d_flag.release(); ix->h_u32a.release(); ix->h_u32b.release(); ix->h_flag.release();
-    for (auto &e : ix->scan_ev) cudaEventDestroy(e);
     if (ix->xchg) {
         Exchange *x = ix->xchg;
         for (int r = 0; r < (int)x->peer_base.size(); ++r)
@@ -1172,10 +1282,6 @@ void orx_destroy(orx_index *ix) {
         cudaFree(x->base);
         delete x;
     }
-    ix->h_myflags.release();
-    ix->h_redo.release();
-    ix->h_done.release();
-    ix->d_counters.release();
     cudaGetLastError();
     delete ix;
 }
@@ -1332,6 +1438,71 @@ int orx_search(orx_index *ix, const float *queries, int nq, int dim, int k, orx_
     return search_locked(ix, queries, nq, k, out_ids, out_dist, out_counts);
 }
 
+namespace {
+int check_search_args(orx_index *ix, const float *queries, int nq, int dim, int k, orx_id *out_ids, double *out_dist,
+                      int *out_counts) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (dim != ORX_DIM) return fail(ORX_ERR_DIM, "different vector dimensions %d and %d", ORX_DIM, dim);
+    if (k < 1 || k > ORX_MAX_K) return fail(ORX_ERR_INVALID, "k must be in [1, %d], got %d", ORX_MAX_K, k);
+    if (nq < 1) return fail(ORX_ERR_INVALID, "nq must be >= 1");
+    if (!queries || !out_ids || !out_dist || !out_counts) return fail(ORX_ERR_INVALID, "null argument");
+    if (ix->group) return fail(ORX_ERR_INVALID, "asynchronous searches are per GPU: a multi-GPU index answers orx_search");
+    return ORX_OK;
+}
+}  // namespace
+
+int orx_search_submit(orx_index *ix, const float *queries, int nq, int dim, int k, orx_id *out_ids, double *out_dist,
+                      int *out_counts, int *ticket) {
+    int rc = check_search_args(ix, queries, nq, dim, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK) return rc;
+    if (!ticket) return fail(ORX_ERR_INVALID, "ticket is null");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    rc = claim_slot(ix, ticket);
+    if (rc != ORX_OK) return rc;
+    rc = search_submit_locked(ix, queries, nq, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK) return rc;
+    ix->cur->pend.ticket = ix->tickets;
+    ix->tickets += 1;
+    return ORX_OK;
+}
+
+int orx_search_wait(orx_index *ix, int ticket) {
+    if (!ix) return fail(ORX_ERR_INVALID, "index is null");
+    if (ix->group) return fail(ORX_ERR_INVALID, "asynchronous searches are per GPU");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    SearchSlot *sl = &ix->slot[(uint32_t)ticket & 1u];
+    if (!sl->pend.active || (sl->pend.ticket & 0x7FFFFFFFu) != (uint32_t)ticket)
+        return fail(ORX_ERR_INVALID, "ticket %d is not in flight", ticket);
+    ix->cur = sl;
+    if (sl->pend.sharded) {
+        if (!ix->xchg || !ix->xchg->connected) return fail(ORX_ERR_INVALID, "shard exchange not connected");
+        return sharded_wait_locked(ix, ix->xchg);
+    }
+    return search_wait_locked(ix);
+}
+
+int orx_search_sharded_submit(orx_index *ix, const float *queries, int nq, int dim, int k, orx_id *out_ids,
+                              double *out_dist, int *out_counts, int *ticket) {
+    int rc = check_search_args(ix, queries, nq, dim, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK) return rc;
+    if (!ticket) return fail(ORX_ERR_INVALID, "ticket is null");
+    std::lock_guard<std::mutex> lk(ix->mu);
+    DeviceGuard g(ix->device);
+    if (!ix->xchg || !ix->xchg->connected) return fail(ORX_ERR_INVALID, "shard exchange not connected (orx_shard_export / orx_shard_connect)");
+    if ((size_t)ix->xchg->world * k > 1024) return fail(ORX_ERR_INVALID, "sharded search: world * k must be <= 1024");
+    const int qchunk = k <= 32 ? XQ_MAX : XQ_MAX * 32 / k;
+    if (nq > qchunk) return fail(ORX_ERR_INVALID, "an asynchronous sharded search takes at most %d queries at k = %d", qchunk, k);
+    rc = claim_slot(ix, ticket);
+    if (rc != ORX_OK) return rc;
+    rc = sharded_submit_locked(ix, ix->xchg, queries, nq, k, out_ids, out_dist, out_counts);
+    if (rc != ORX_OK) return rc;
+    ix->cur->pend.ticket = ix->tickets;
+    ix->tickets += 1;
+    return ORX_OK;
+}
+
 int orx_search_filtered(orx_index *ix, const float *queries, int nq, int dim, int k, const orx_id *allow_ids,
                         uint64_t n_allow, orx_id *out_ids, double *out_dist, int *out_counts) {
     int rc = check_filtered_args(ix, queries, nq, dim, k, out_ids, out_dist, out_counts);
@@ -1341,6 +1512,7 @@ int orx_search_filtered(orx_index *ix, const float *queries, int nq, int dim, in
     if (ix->group) return group_search_filtered(ix->group, queries, nq, k, allow_ids, n_allow, out_ids, out_dist, out_counts);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
+    if (any_in_flight(ix)) return fail(ORX_ERR_INVALID, "wait for the searches in flight (orx_search_wait) first");
     std::vector<uint32_t> rows;
     resolve_allow_ids(ix, allow_ids, n_allow, rows);
     rc = upload_filter(ix, rows, ix->fb_list, ix->fb_count, ix->allow_bits);
@@ -1382,6 +1554,7 @@ int orx_search_with_filter(orx_index *ix, orx_filter *f, const float *queries, i
     if (!f || f->ix != ix) return fail(ORX_ERR_INVALID, "filter does not belong to this index");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
+    if (any_in_flight(ix)) return fail(ORX_ERR_INVALID, "wait for the searches in flight (orx_search_wait) first");
     if (!f->resolved || f->generation != ix->generation) {
         // the id -> row map changed since the bitmap was built (upsert of new ids, delete, import)
         std::vector<uint32_t> rows;
@@ -1631,11 +1804,12 @@ int orx_debug_coarse_scores(orx_index *ix, const float *queries, int nq, int use
     if (!is_device_ptr(out_device)) return fail(ORX_ERR_INVALID, "out must be device memory");
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
-    if (!ix->umma || ix->n_live == 0) return fail(ORX_ERR_INVALID, "empty table");
+    if (any_in_flight(ix)) return fail(ORX_ERR_INVALID, "wait for the searches in flight (orx_search_wait) first");
+    if (!ix->cur->umma || ix->n_live == 0) return fail(ORX_ERR_INVALID, "empty table");
     const float *q_src = nullptr;
     int rc = stage_queries(ix, queries, nq, &q_src);
     if (rc != ORX_OK) return rc;
-    rc = orx::umma_dump_scores(ix->umma, ix->dtype, ix->table, ix->scale, (uint32_t)ix->n_live, ix->qhat.p, ix->qhat16.p, nq,
+    rc = orx::umma_dump_scores(ix->cur->umma, ix->dtype, ix->table, ix->scale, (uint32_t)ix->n_live, ix->cur->qhat.p, ix->cur->qhat16.p, nq,
                                use_pairs != 0, out_device, ix->stream);
     if (rc != ORX_OK) return fail(rc, "tcgen05 dump failed: %s", orx::umma_last_error());
     ix->stats.kernel_launches += 2;

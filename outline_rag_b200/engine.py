@@ -342,6 +342,22 @@ class Index:
         check(lib.orx_debug_coarse_scores(self._h, C.c_void_p(ptr), nq, int(bool(use_pairs)), C.c_void_p(out.data_ptr())))
         return out
 
+    # -- two searches in flight (orx_search_submit / orx_search_wait)
+    def search_submit(self, queries, k: int, out, sharded: bool = False) -> int:
+        """Launch a search of a float32 CUDA tensor `queries` into the caller-owned CUDA tensors `out` =
+        (ids int64 [nq,k,2], dist float64 [nq,k], counts int32 [nq]) and return a ticket at once; at most two
+        tickets may be outstanding.  `search_wait(ticket)` completes it (`out` is filled then).  `sharded=True`:
+        the collective row-sharded search (every rank submits and waits in the same order)."""
+        q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+        t = C.c_int(-1)
+        fn = lib.orx_search_sharded_submit if sharded else lib.orx_search_submit
+        check(fn(self._h, C.c_void_p(q.data_ptr()), q.shape[0], q.shape[1], int(k), C.c_void_p(out[0].data_ptr()),
+                 C.c_void_p(out[1].data_ptr()), C.c_void_p(out[2].data_ptr()), C.byref(t)))
+        return int(t.value)
+
+    def search_wait(self, ticket: int) -> None:
+        check(lib.orx_search_wait(self._h, int(ticket)))
+
     def make_filter(self, allow_ids) -> Filter:
         return Filter(self, allow_ids)
 

@@ -199,6 +199,28 @@ class ShardedIndex:
             return ids, dist_, cnt
         return self._gather_merge(ids, dist_, cnt, k)
 
+    # -- throughput mode: two searches in flight (device tensors only)
+    def search_submit(self, queries, k: int = 12):
+        """Launch a (collective) search of a float32 CUDA tensor and return `(ticket, out)`; `search_wait(ticket)`
+        completes it and `out` = (ids, dist, counts) CUDA tensors is valid afterwards.  At most two tickets may be
+        outstanding, waited for in submission order (on every rank alike).  The output tensors alternate between two
+        cached sets per (nq, k): a result is overwritten by the submit after next."""
+        q = queries if queries.dim() == 2 else queries.unsqueeze(0)
+        self._submits = getattr(self, "_submits", 0)
+        key = (q.shape[0], k, self._submits & 1)
+        self._submits += 1
+        out = self._outs.get(key)
+        if out is None:
+            out = self._outs[key] = (torch.empty((q.shape[0], k, 2), dtype=torch.int64, device=q.device),
+                                     torch.empty((q.shape[0], k), dtype=torch.float64, device=q.device),
+                                     torch.empty((q.shape[0],), dtype=torch.int32, device=q.device))
+        if self.world > 1 and self.exchange != "p2p":
+            raise RuntimeError("search_submit needs the peer-memory exchange (or a single rank)")
+        return self.local.search_submit(q, k, out, sharded=self.world > 1), out
+
+    def search_wait(self, ticket: int) -> None:
+        self.local.search_wait(ticket)
+
     def search_filtered(self, queries, k: int, allow_ids):
         """COLLECTIVE filtered search (`WHERE langchain_id IN (...)`, see Index.search_filtered): every rank
         resolves the predicate against its own shard -- it is handed only the ids it owns -- and the k

@@ -754,3 +754,64 @@ def test_large_k_for_a_wider_reranker_feed(Index, small_table):
         ix.upsert(ids[:50], Xd[:50])
         g = ix.search(Q[:2], 128)
         assert (g[2] == 50).all()
+
+
+def test_two_searches_in_flight_equal_the_synchronous_answers(Index, small_table):
+    """orx_search_submit / orx_search_wait: two complete scratch sets, so query i+1 is launched while query i is still in
+    flight.  Same answers as orx_search (bit for bit), also when a query needs the exact fallback, when writes land
+    between submit and wait of other tickets, and the bookkeeping errors are reported."""
+    import torch
+    import outline_rag_b200 as orx
+    X, Q, _ = small_table
+    ids = _ids(X.shape[0])
+    with Index("fp32") as ix:
+        ix.upsert(ids, X)
+        dup = np.tile(X[7], (300, 1))                               # a flood of exact ties: query 7's row needs the exact path
+        ix.upsert(_ids(300, 500_000), dup)
+        allX, all_ids = np.concatenate([X, dup]), np.concatenate([ids, _ids(300, 500_000)])
+        Qd = torch.from_numpy(np.concatenate([Q[:6], X[7:8]])).cuda()
+        want = [ix.search(Qd[i:i + 1].cpu().numpy(), K) for i in range(7)]
+        outs = [(torch.empty((1, K, 2), dtype=torch.int64, device="cuda"), torch.empty((1, K), dtype=torch.float64, device="cuda"),
+                 torch.empty((1,), dtype=torch.int32, device="cuda")) for _ in range(2)]
+        prev = None
+        got = {}
+        for i in range(7):
+            t = ix.search_submit(Qd[i:i + 1], K, outs[i & 1])
+            if prev is not None:
+                ix.search_wait(prev[0])
+                got[prev[1]] = tuple(o.cpu().numpy() for o in outs[prev[1] & 1])
+            prev = (t, i)
+        ix.search_wait(prev[0])
+        got[prev[1]] = tuple(o.cpu().numpy() for o in outs[prev[1] & 1])
+        for i in range(7):
+            assert np.array_equal(got[i][0].view(np.uint64), want[i][0]), i
+            assert np.array_equal(got[i][1].view(np.uint64), want[i][1].view(np.uint64)), i
+        w_ids, _ = O.topk_exact(allX, all_ids, X[7], K)
+        assert np.array_equal(got[6][0][0].view(np.uint64), w_ids) and ix.stats()["fallback_exhaustive"] > 0
+        # batches (tcgen05 path) in flight, a write between the submits: each search sees the table of its submit time
+        Qb = torch.from_numpy(Q[:24]).cuda()
+        ob = [(torch.empty((24, K, 2), dtype=torch.int64, device="cuda"), torch.empty((24, K), dtype=torch.float64, device="cuda"),
+               torch.empty((24,), dtype=torch.int32, device="cuda")) for _ in range(2)]
+        before = ix.search(Q[:24], K)
+        t0 = ix.search_submit(Qb, K, ob[0])
+        victims = before[0][:, 0].copy()
+        assert ix.delete(victims) == len({tuple(v) for v in victims.tolist()})
+        t1 = ix.search_submit(Qb, K, ob[1])
+        ix.search_wait(t0)
+        ix.search_wait(t1)
+        assert np.array_equal(ob[0][0].cpu().numpy().view(np.uint64), before[0])
+        after = ix.search(Q[:24], K)
+        assert np.array_equal(ob[1][0].cpu().numpy().view(np.uint64), after[0])
+        assert not np.isin(after[0][:, :, 1], victims[:, 1]).any()
+        # bookkeeping
+        a = ix.search_submit(Qd[:1], K, outs[0])
+        b = ix.search_submit(Qd[1:2], K, outs[1])
+        with pytest.raises(orx.OrxValueError, match="two searches are in flight"):
+            ix.search_submit(Qd[2:3], K, outs[0])
+        with pytest.raises(orx.OrxValueError, match="in flight"):
+            ix.search_filtered(Q[:1], K, ids[:10])
+        ix.search_wait(a)
+        with pytest.raises(orx.OrxValueError, match="not in flight"):
+            ix.search_wait(a)
+        ix.search_wait(b)
+        assert ix.search(Q[:1], K)[2][0] == K

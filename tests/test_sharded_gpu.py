@@ -82,6 +82,21 @@ def _worker(rank, world, port, out_dir):
             if mode == "p2p":
                 h = sh.search(Q[:3], K)                       # host buffers through the C-ABI
                 res["p2p_host_ids"] = h[0]
+                # two collective searches in flight (orx_search_sharded_submit / orx_search_wait), incl. a query whose
+                # shard-local candidates are a flood of exact ties (second, exact round while another search is in flight)
+                sh.upsert(O.ids_arange(900_000, 900_300), np.tile(X[7], (300, 1)))
+                qs = torch.from_numpy(np.concatenate([Q[:5], X[7:8], Q[5:8]])).cuda()
+                piped, prev = [], None
+                for i in range(qs.shape[0]):
+                    t, out = sh.search_submit(qs[i:i + 1], K)
+                    if prev is not None:
+                        sh.search_wait(prev[0])
+                        piped.append(prev[1][0].cpu().numpy().view(np.uint64).copy())
+                    prev = (t, out)
+                sh.search_wait(prev[0])
+                piped.append(prev[1][0].cpu().numpy().view(np.uint64).copy())
+                res["p2p_piped_ids"] = np.concatenate(piped)
+                sh.delete(O.ids_arange(900_000, 900_300))
                 sh.delete(ids[100:160])
                 got = sh.search(qd[:4], K)
                 res["p2p_after_delete_ids"] = got[0].cpu().numpy().view(np.uint64).copy()
@@ -107,6 +122,11 @@ def test_two_gpus_p2p_and_nccl_equal_the_oracle(tmp_path):
     r = [np.load(tmp_path / f"r{i}.npz") for i in range(2)]
     keep = np.ones(n, bool)
     keep[100:160] = False
+    dupX = np.concatenate([X, np.tile(X[7], (300, 1))])
+    dup_ids = np.concatenate([ids, O.ids_arange(900_000, 900_300)])
+    w7, _ = O.topk_exact(dupX, dup_ids, X[7], K)
+    for rr in r:
+        assert np.array_equal(rr["p2p_piped_ids"][5], w7), "the query that needed the exact second round"
     for qi in range(70):
         w_ids, w_d = O.topk_exact(X, ids, Q[qi], K)
         for rr in r:
@@ -117,6 +137,8 @@ def test_two_gpus_p2p_and_nccl_equal_the_oracle(tmp_path):
                 assert np.array_equal(rr["p2p_ids_1"][0], w_ids) and np.array_equal(rr["nccl_ids_1"][0], w_ids)
             if qi < 3:
                 assert np.array_equal(rr["p2p_host_ids"][qi], w_ids)
+            if qi < 8:
+                assert np.array_equal(rr["p2p_piped_ids"][qi if qi < 5 else qi + 1], w_ids), ("two in flight", qi)
             if qi < 4:
                 w2, _ = O.topk_exact(X[keep], ids[keep], Q[qi], K)
                 assert np.array_equal(rr["p2p_after_delete_ids"][qi], w2)
