@@ -138,7 +138,8 @@ def test_two_gpus_p2p_and_nccl_equal_the_oracle(tmp_path):
             if qi < 3:
                 assert np.array_equal(rr["p2p_host_ids"][qi], w_ids)
             if qi < 8:
-                assert np.array_equal(rr["p2p_piped_ids"][qi if qi < 5 else qi + 1], w_ids), ("two in flight", qi)
+                wp, _ = O.topk_exact(dupX, dup_ids, Q[qi], K)       # (the tie flood is in the table during these searches)
+                assert np.array_equal(rr["p2p_piped_ids"][qi if qi < 5 else qi + 1], wp), ("two in flight", qi)
             if qi < 4:
                 w2, _ = O.topk_exact(X[keep], ids[keep], Q[qi], K)
                 assert np.array_equal(rr["p2p_after_delete_ids"][qi], w2)
