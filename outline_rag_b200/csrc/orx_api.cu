@@ -177,6 +177,9 @@ struct SearchSlot {         // everything ONE search in flight owns
     // the search in flight in this slot (orx_search_submit ... orx_search_wait)
     struct Pending {
         bool active = false, complete = false, sharded = false, out_on_dev = false;
+        bool settled = false;               // completed early by a write that had to wait for it; `settled_rc` is its verdict
+        int settled_rc = ORX_OK;
+        std::string settled_err;
         int nq = 0, k = 0, path = 1;
         orx_id *out_ids = nullptr;
         double *out_dist = nullptr;
@@ -754,6 +757,10 @@ int search_wait_locked(orx_index *ix) {
     SearchSlot::Pending &pd = ix->cur->pend;
     if (!pd.active) return fail(ORX_ERR_INVALID, "no search in flight under this ticket");
     pd.active = false;
+    if (pd.settled) {
+        if (pd.settled_rc != ORX_OK) g_err = pd.settled_err;
+        return pd.settled_rc;
+    }
     const int nq = pd.nq, k = pd.k;
     if (!pd.complete) {
         const size_t nk = (size_t)nq * k;
@@ -1074,6 +1081,10 @@ int sharded_wait_locked(orx_index *ix, Exchange *x) {
     SearchSlot::Pending &pd = ix->cur->pend;
     if (!pd.active || !pd.sharded) return fail(ORX_ERR_INVALID, "no sharded search in flight under this ticket");
     pd.active = false;
+    if (pd.settled) {
+        if (pd.settled_rc != ORX_OK) g_err = pd.settled_err;
+        return pd.settled_rc;
+    }
     cudaStream_t st = ix->stream;
     const int nq = pd.nq, k = pd.k;
     const size_t nk = (size_t)nq * k;
@@ -1152,6 +1163,26 @@ int search_sharded_locked(orx_index *ix, Exchange *x, const float *queries, int 
     if (rc != ORX_OK) return rc;
     ix->tickets += 1;
     return sharded_wait_locked(ix, x);
+}
+
+// A write (upsert / delete / import) is ordered AFTER every search submitted before it: the searches in flight are
+// completed here -- including the exact re-answer of queries the fast path could not prove, which must see the table as
+// it was -- in ticket order, their verdicts kept for the caller's orx_search_wait.  (Output buffers given at submit are
+// filled now; they have to stay valid until the wait anyway.)
+void settle_in_flight(orx_index *ix) {
+    SearchSlot *order[2] = {&ix->slot[ix->tickets & 1u], &ix->slot[(ix->tickets + 1u) & 1u]};     // older ticket first
+    for (SearchSlot *sl : order) {
+        SearchSlot::Pending &pd = sl->pend;
+        if (!pd.active || pd.settled) continue;
+        ix->cur = sl;
+        const std::string keep = g_err;
+        const int rc = pd.sharded ? (ix->xchg ? sharded_wait_locked(ix, ix->xchg) : ORX_ERR_INVALID) : search_wait_locked(ix);
+        pd.settled = true;
+        pd.settled_rc = rc;
+        pd.settled_err = g_err;
+        pd.active = true;                   // still owed to the caller
+        g_err = keep;
+    }
 }
 
 #include "group.inl"
@@ -1360,6 +1391,7 @@ int orx_upsert(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t n, 
     if (ix->group) return group_upsert(ix->group, ids, vecs, n);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
+    settle_in_flight(ix);
     return upsert_locked(ix, ids, vecs, n, /*validate=*/true);
 }
 
@@ -1371,6 +1403,7 @@ int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed
     if (ix->group) return group_delete(ix->group, ids, n, n_removed);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
+    settle_in_flight(ix);
     cudaStream_t st = ix->stream;
 
     std::vector<uint32_t> doomed;
@@ -1661,6 +1694,7 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
     if (ix->group) return group_import_rows(ix->group, ids, rows_raw, n);
     std::lock_guard<std::mutex> lk(ix->mu);
     DeviceGuard g(ix->device);
+    settle_in_flight(ix);
     cudaStream_t st = ix->stream;
     {   // every id must be new: this is an append, not an upsert
         std::unordered_map<orx_id, int, IdHash, IdEq> seen;
