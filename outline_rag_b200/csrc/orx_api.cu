@@ -57,6 +57,87 @@ struct IdEq {
     bool operator()(const orx_id &a, const orx_id &b) const { return a.hi == b.hi && a.lo == b.lo; }
 };
 
+// chunk id -> row: open addressing with linear probing over a power-of-two table kept at most half full (one cache line
+// per look-up in the common case; std::unordered_map's node-per-entry layout cost ~150 ns per operation, which was the
+// largest host term of an upsert / delete / filter resolution / cold-start batch).  Deletions leave tombstones that the
+// next rehash drops.
+class IdMap {
+    struct Entry {
+        orx_id id;
+        uint32_t row;
+        uint32_t state;          // 0 empty, 1 used, 2 tombstone
+    };
+    std::vector<Entry> tab_;
+    size_t used_ = 0, filled_ = 0;   // live entries / live + tombstones
+    static size_t hash(const orx_id &a) { return IdHash()(a); }
+    void rehash(size_t want_entries) {
+        size_t cap = 64;
+        while (cap < want_entries * 2) cap <<= 1;
+        std::vector<Entry> old;
+        old.swap(tab_);
+        tab_.assign(cap, Entry{{0, 0}, 0, 0});
+        used_ = filled_ = 0;
+        for (const Entry &e : old)
+            if (e.state == 1) set(e.id, e.row);
+    }
+
+public:
+    size_t size() const { return used_; }
+    void reserve(size_t n) {
+        if (tab_.size() < n * 2) rehash(n);
+    }
+    void clear() {
+        for (Entry &e : tab_) e.state = 0;
+        used_ = filled_ = 0;
+    }
+    const uint32_t *find(const orx_id &id) const {
+        if (tab_.empty()) return nullptr;
+        const size_t mask = tab_.size() - 1;
+        for (size_t i = hash(id) & mask;; i = (i + 1) & mask) {
+            const Entry &e = tab_[i];
+            if (e.state == 0) return nullptr;
+            if (e.state == 1 && e.id.hi == id.hi && e.id.lo == id.lo) return &e.row;
+        }
+    }
+    void set(const orx_id &id, uint32_t row) {          // insert or assign
+        if ((filled_ + 1) * 2 > tab_.size()) rehash(std::max<size_t>(used_ + 1, 32) * 2);
+        const size_t mask = tab_.size() - 1;
+        size_t grave = (size_t)-1;
+        for (size_t i = hash(id) & mask;; i = (i + 1) & mask) {
+            Entry &e = tab_[i];
+            if (e.state == 1) {
+                if (e.id.hi == id.hi && e.id.lo == id.lo) {
+                    e.row = row;
+                    return;
+                }
+            } else if (e.state == 2) {
+                if (grave == (size_t)-1) grave = i;
+            } else {
+                Entry &dst = grave != (size_t)-1 ? tab_[grave] : e;
+                if (grave == (size_t)-1) ++filled_;
+                dst.id = id;
+                dst.row = row;
+                dst.state = 1;
+                ++used_;
+                return;
+            }
+        }
+    }
+    bool erase(const orx_id &id) {
+        if (tab_.empty()) return false;
+        const size_t mask = tab_.size() - 1;
+        for (size_t i = hash(id) & mask;; i = (i + 1) & mask) {
+            Entry &e = tab_[i];
+            if (e.state == 0) return false;
+            if (e.state == 1 && e.id.hi == id.hi && e.id.lo == id.lo) {
+                e.state = 2;
+                --used_;
+                return true;
+            }
+        }
+    }
+};
+
 bool is_device_ptr(const void *p) {
     if (!p) return false;
     cudaPointerAttributes at;
@@ -216,7 +297,7 @@ struct orx_index {
 
     // host mirror of the id column + id -> row map
     std::vector<orx_id> host_row_ids;
-    std::unordered_map<orx_id, uint32_t, IdHash, IdEq> map;
+    IdMap map;
 
     // search scratch: TWO complete sets, so that one search can be launched while the previous one is still in flight
     // (orx_search_submit / orx_search_wait); `cur` = the set the search being submitted / completed works on
@@ -368,52 +449,55 @@ int upsert_locked(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t 
         if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
     }
 
-    // room for every id that is new (existing id -> its row, new id -> append; last duplicate wins)
-    uint64_t n_new = 0;
-    {
-        std::unordered_map<orx_id, int, IdHash, IdEq> seen;
-        if (n > 1) seen.reserve(n);
-        for (uint64_t i = 0; i < n; ++i)
-            if (ix->map.find(ids[i]) == ix->map.end() && seen.emplace(ids[i], 1).second) ++n_new;
-    }
-    int rc = grow_table(ix, ix->n_live + n_new);
-    if (rc != ORX_OK) return rc;
-
     CK(ix->d_src_idx.ensure(chunk));
     CK(ix->d_dst_row.ensure(chunk));
     CK(ix->d_ids.ensure(chunk));
     CK(ix->h_u32a.ensure(chunk));
     CK(ix->h_u32b.ensure(chunk));
-    std::unordered_map<orx_id, uint32_t, IdHash, IdEq> pending;      // ids new in this chunk -> row (published after the sync)
+    IdMap pending;                                                   // ids new in this chunk -> row (published after the sync)
+    std::vector<std::pair<orx_id, uint32_t>> pending_list;
     std::unordered_map<uint32_t, uint32_t> slot_of_row;              // dst row -> plan slot
     for (uint64_t s = 0; s < n; s += chunk) {
         const uint64_t m = std::min(chunk, n - s);
+        // plan: existing id -> its row, new id -> append; an id repeated inside the chunk keeps the later source row
         pending.clear();
+        pending.reserve(m);
+        pending_list.clear();
         slot_of_row.clear();
         uint32_t np = 0;
         uint64_t next_row = ix->n_live;
+        bool repeats = false;
         for (uint64_t i = 0; i < m; ++i) {
             const orx_id id = ids[s + i];
             uint32_t row;
-            auto it = ix->map.find(id);
-            if (it != ix->map.end()) row = it->second;
+            bool fresh = false;
+            if (const uint32_t *r = ix->map.find(id)) row = *r;
+            else if (const uint32_t *r2 = pending.find(id)) row = *r2;
             else {
-                auto pit = pending.find(id);
-                if (pit != pending.end()) row = pit->second;
-                else {
-                    row = (uint32_t)next_row++;
-                    pending.emplace(id, row);
+                row = (uint32_t)next_row++;
+                pending.set(id, row);
+                pending_list.emplace_back(id, row);
+                fresh = true;
+            }
+            if (!fresh) {
+                // a row written before: by an earlier element of this chunk (the later source row wins) or not at all yet
+                if (!repeats) {                                       // build the row -> slot index lazily: rare path
+                    for (uint32_t p = 0; p < np; ++p) slot_of_row.emplace(ix->h_u32b.p[p], p);
+                    repeats = true;
+                }
+                auto ps = slot_of_row.find(row);
+                if (ps != slot_of_row.end()) {
+                    ix->h_u32a.p[ps->second] = (uint32_t)i;
+                    continue;
                 }
             }
-            auto ps = slot_of_row.find(row);
-            if (ps != slot_of_row.end()) ix->h_u32a.p[ps->second] = (uint32_t)i;     // the later source row wins
-            else {
-                slot_of_row.emplace(row, np);
-                ix->h_u32a.p[np] = (uint32_t)i;
-                ix->h_u32b.p[np] = row;
-                ++np;
-            }
+            if (repeats) slot_of_row.emplace(row, np);
+            ix->h_u32a.p[np] = (uint32_t)i;
+            ix->h_u32b.p[np] = row;
+            ++np;
         }
+        int rc = grow_table(ix, next_row);                            // room for the ids that are new
+        if (rc != ORX_OK) return rc;
         const float *src = vecs + s * ORX_DIM;
         if (!on_dev) {
             CK(cudaMemcpyAsync(ix->stage.p, src, m * ORX_DIM * sizeof(float), cudaMemcpyHostToDevice, st));
@@ -434,10 +518,10 @@ int upsert_locked(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t 
         CK(cudaGetLastError());
         if (*ix->h_flag.p) return fail(ORX_ERR_NONFINITE, "NaN or infinite value not allowed in vector");
         // ---- the device holds the rows: publish them
-        if (!pending.empty()) {
+        if (!pending_list.empty()) {
             if (ix->host_row_ids.size() < next_row) ix->host_row_ids.resize(next_row);
-            for (const auto &kv : pending) {
-                ix->map.emplace(kv.first, kv.second);
+            for (const auto &kv : pending_list) {
+                ix->map.set(kv.first, kv.second);
                 ix->host_row_ids[kv.second] = kv.first;
             }
             ix->n_live = next_row;
@@ -839,8 +923,7 @@ void resolve_allow_ids(const orx_index *ix, const orx_id *ids, uint64_t n, std::
     rows.clear();
     rows.reserve(n);
     for (uint64_t i = 0; i < n; ++i) {
-        auto it = ix->map.find(ids[i]);
-        if (it != ix->map.end()) rows.push_back(it->second);
+        if (const uint32_t *r = ix->map.find(ids[i])) rows.push_back(*r);
     }
     std::sort(rows.begin(), rows.end());
     rows.erase(std::unique(rows.begin(), rows.end()), rows.end());
@@ -1379,7 +1462,7 @@ int orx_contains(const orx_index *ix, orx_id id) {
     if (!ix) return 0;
     if (ix->group) return orx_contains(ix->group->shards[shard_of_id(id, (uint32_t)ix->group->shards.size())], id);
     std::lock_guard<std::mutex> lk(ix->mu);
-    return ix->map.find(id) != ix->map.end() ? 1 : 0;
+    return ix->map.find(id) != nullptr ? 1 : 0;
 }
 
 int orx_upsert(orx_index *ix, const orx_id *ids, const float *vecs, uint64_t n, int dim) {
@@ -1409,10 +1492,10 @@ int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed
     std::vector<uint32_t> doomed;
     doomed.reserve(n);
     for (uint64_t i = 0; i < n; ++i) {
-        auto it = ix->map.find(ids[i]);
-        if (it == ix->map.end()) continue;        // unknown id: ignored, like the SQL DELETE
-        doomed.push_back(it->second);
-        ix->map.erase(it);                        // also drops a repeated id in the same call
+        const uint32_t *r = ix->map.find(ids[i]);
+        if (!r) continue;                         // unknown id: ignored, like the SQL DELETE
+        doomed.push_back(*r);
+        ix->map.erase(ids[i]);                    // also drops a repeated id in the same call
     }
     const uint64_t d = doomed.size();
     if (d == 0) return ORX_OK;
@@ -1434,7 +1517,7 @@ int orx_delete(orx_index *ix, const orx_id *ids, uint64_t n, uint64_t *n_removed
         ix->h_u32b.p[hmv] = dst;
         const orx_id moved = ix->host_row_ids[r];
         ix->host_row_ids[dst] = moved;
-        ix->map[moved] = dst;
+        ix->map.set(moved, dst);
         ++hmv;
     }
     ix->host_row_ids.resize(new_live);
@@ -1700,7 +1783,7 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
         std::unordered_map<orx_id, int, IdHash, IdEq> seen;
         seen.reserve(n);
         for (uint64_t i = 0; i < n; ++i)
-            if (ix->map.find(ids[i]) != ix->map.end() || !seen.emplace(ids[i], 1).second)
+            if (ix->map.find(ids[i]) != nullptr || !seen.emplace(ids[i], 1).second)
                 return fail(ORX_ERR_INVALID, "orx_import_rows: id %llu of the batch is already present", (unsigned long long)i);
     }
     int rc = grow_table(ix, ix->n_live + n);
@@ -1725,7 +1808,7 @@ int orx_import_rows(orx_index *ix, const orx_id *ids, const void *rows_raw, uint
     ix->host_row_ids.resize(row0 + n);
     for (uint64_t i = 0; i < n; ++i) {
         ix->host_row_ids[row0 + i] = ids[i];
-        ix->map.emplace(ids[i], (uint32_t)(row0 + i));
+        ix->map.set(ids[i], (uint32_t)(row0 + i));
     }
     ix->n_live = row0 + n;
     ix->generation += 1;
@@ -1867,9 +1950,9 @@ int orx_fetch(orx_index *ix, const orx_id *ids, uint64_t n, float *out_vecs, int
     for (uint64_t s = 0; s < n; s += chunk) {
         const uint64_t m = std::min(chunk, n - s);
         for (uint64_t i = 0; i < m; ++i) {
-            auto it = ix->map.find(ids[s + i]);
-            out_found[s + i] = it != ix->map.end();
-            ix->h_u32a.p[i] = it != ix->map.end() ? it->second : 0xFFFFFFFFu;
+            const uint32_t *r = ix->map.find(ids[s + i]);
+            out_found[s + i] = r != nullptr;
+            ix->h_u32a.p[i] = r ? *r : 0xFFFFFFFFu;
         }
         CK(cudaMemcpyAsync(ix->d_src_idx.p, ix->h_u32a.p, m * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         orx::launch_gather_rows(ix->dtype, ix->table, ix->d_src_idx.p, (uint32_t)m, ix->stage.p, st);
