@@ -196,12 +196,27 @@ finalize_kernel(const T *__restrict__ table, const double *__restrict__ n2,
     __shared__ uint64_t s_all[FIN_SORT_MAX];
     const int total_keys = nparts * K;
     if (!fast && total_keys <= FIN_SORT_MAX) {
-        // 1c (unsorted lists that fit shared memory, i.e. the tcgen05 scan at large batches): bitonic sort
-        //     of all keys, descending; the first K are the query's candidates.
-        int n = 64;
-        while (n < total_keys) n <<= 1;
+        // 1c (unsorted lists that fit shared memory, i.e. the tcgen05 scan at large batches): the lists are mostly
+        //     EMPTY slots (a list holds only the rows that passed its CTA's running threshold), so the non-empty keys
+        //     are compacted first and the bitonic sort runs over the next power of two of THEIR number (typically 256-512
+        //     instead of 2048 slots); descending; the first K are the query's candidates.
+        __shared__ int s_nkeys;
+        if (threadIdx.x == 0) s_nkeys = 0;
         __syncthreads();
-        for (int i = threadIdx.x; i < n; i += FIN_THREADS) s_all[i] = i < total_keys ? partial[i] : 0ull;
+        for (int i0 = 0; i0 < total_keys; i0 += FIN_THREADS) {
+            const int i = i0 + threadIdx.x;
+            const uint64_t key = i < total_keys ? partial[i] : 0ull;
+            const unsigned m = __ballot_sync(FULL_MASK, key != 0ull);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_nkeys, __popc(m));
+            base = __shfl_sync(FULL_MASK, base, 0);
+            if (key != 0ull) s_all[base + __popc(m & ((1u << lane) - 1u))] = key;
+        }
+        __syncthreads();
+        const int nkeys = s_nkeys;
+        int n = 64;
+        while (n < nkeys || n < K) n <<= 1;               // the first K sorted entries are read below
+        for (int i = nkeys + threadIdx.x; i < n; i += FIN_THREADS) s_all[i] = 0ull;
         __syncthreads();
         for (int size = 2; size <= n; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
