@@ -28,7 +28,9 @@ extern "C" {
 
 #define ORX_DIM 1024            /* VECTOR_DIM, reference app/config.py:8 */
 #define ORX_MAX_K 128           /* TOP_K is 12 (reference app/config.py:253); up to 128 for a wider
-                                   reranker feed.  k > 32 always runs the fp32 scan. */
+                                   reranker feed.  Batches with k <= 64 run the tcgen05 scan
+                                   (64-key candidate lists up to k = 16, 160-key lists beyond); k > 64 runs
+                                   one fp32 scan per query. */
 
 #define ORX_DTYPE_F32 0         /* rows stored verbatim (fp32) + per-row 1/norm   */
 #define ORX_DTYPE_BF16 1        /* rows stored as RNE-bf16 of the normalised row  */
@@ -147,7 +149,10 @@ int orx_search_sharded_submit(orx_index *idx, const float *queries, int nq, int 
  * are each rescored canonically (no scan; O(n_allow) row reads per query).  From 4096 eligible rows on
  * the predicate becomes a row bitmap and the sequential scan skips the rows whose bit is clear (HBM
  * traffic = eligible rows only), with the same candidate proof as orx_search; an unproven query falls
- * back to the rescoring path.  Exact either way.  Same outputs and ordering as orx_search. */
+ * back to the rescoring path.  A BATCH with nq x eligible rows >= rows runs ONE tcgen05 pass over the
+ * table instead of nq bitmap scans: the predicate is folded into the per-row scale the epilogue
+ * multiplies with (an excluded row can never be a candidate).  Exact either way.  Same outputs and
+ * ordering as orx_search. */
 int orx_search_filtered(orx_index *idx, const float *queries, int nq, int dim, int k,
                         const orx_id *allow_ids, uint64_t n_allow,
                         orx_id *out_ids, double *out_dist, int *out_counts);

@@ -16,6 +16,8 @@
 
 #ifdef ORX_GROUP_TYPES      // first inclusion (global scope): the types
 
+constexpr int WORKER_SPIN_MS = 8;      // longer than one search of a 10M-row table on one GPU
+
 struct Worker {
     int device = 0;
     std::vector<int> shards;                 // indices into Group::shards
@@ -32,15 +34,20 @@ struct Worker {
         cudaSetDevice(device);
         uint64_t seen = 0;
         for (;;) {
-            // spin briefly (a closed loop of searches re-posts within microseconds), then sleep
+            // spin for a few milliseconds (a loop of searches re-posts one search time later -- 0.75 ms at 8 GPUs, 5.6 ms
+            // on one -- and a condition-variable wake-up costs 30-60 us of every search it hits), then sleep
             int spins = 0;
+            std::chrono::steady_clock::time_point t_idle{};
             while (posted.load(std::memory_order_acquire) == seen && !quit.load(std::memory_order_relaxed)) {
-                if (++spins < 20000) {
+                if ((++spins & 63) != 0) {
 #if defined(__x86_64__)
                     __builtin_ia32_pause();
 #endif
                     continue;
                 }
+                const auto now = std::chrono::steady_clock::now();
+                if (spins == 64) t_idle = now;
+                if (now - t_idle < std::chrono::milliseconds(WORKER_SPIN_MS)) continue;
                 std::unique_lock<std::mutex> lk(m);
                 sleeping.store(true, std::memory_order_seq_cst);
                 cv.wait(lk, [&] { return posted.load(std::memory_order_acquire) != seen || quit.load(); });
@@ -383,9 +390,10 @@ int group_search_chunk(Group *g, const float *queries, int nq, int k, orx_id *ou
         }
     }
     for (int s = 0; s < G; ++s) {
+        g->shards[s]->stats.last_path = paths[s];
+        if (g->shards[s]->cur->scan_ev_used == 0) continue;       // scan timing is off: nothing to read on that device
         DeviceGuard dg(g->shards[s]->device);
         harvest_scan_events(g->shards[s]);
-        g->shards[s]->stats.last_path = paths[s];
     }
     g->last_search_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     g->last_path = paths[0];

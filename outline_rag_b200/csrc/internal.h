@@ -99,6 +99,9 @@ void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t
                       cudaStream_t st);
 
 // the same scan over the rows whose bit is set in allow_bits [(n_rows+31)/32 words; bits >= n_rows are 0]
+int scan_gemv_batch_parts(int device, uint32_t n_rows, int nq);
+void launch_scan_gemv_batch(int dtype, const void *table, const float *scale, uint32_t n_rows, const float *qhat, int nq,
+                            int slots, uint64_t *partial, int parts, cudaStream_t st);
 void launch_scan_gemv_filtered(int dtype, const void *table, const float *scale, uint32_t n_rows,
                                const uint32_t *allow_bits, const float *qhat, int nq, int slots,
                                uint64_t *partial, int grid, cudaStream_t st);
@@ -116,6 +119,7 @@ void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint
                         cudaStream_t st);
 
 // ---- pgwire.cu (pgvector wire formats: COPY BINARY bulk load, text input)
+void launch_mask_scale(const float *scale, const uint32_t *allow_bits, uint32_t n_rows, float *out, cudaStream_t st);
 void launch_decode_pgvector(const uint8_t *raw, const uint64_t *payload_off, uint32_t n, float *out,
                             cudaStream_t st);
 
@@ -144,7 +148,6 @@ template <typename T> inline T cap_grid(T blocks, int ctas_per_sm) {     // pers
 
 // ---- orx_api.cu: what the other translation units need from an index
 int set_error(int code, const char *fmt, ...);     // records the thread-local message, returns code
-cudaStream_t index_stream(const orx_index *ix);
 int index_device(const orx_index *ix);
 void index_count_launches(orx_index *ix, uint64_t n);
 

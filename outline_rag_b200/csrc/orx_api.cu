@@ -310,6 +310,7 @@ struct orx_index {
     struct Group *group = nullptr;       // non-null: this handle is a multi-GPU group (orx_create_multi); shard fields unused
     // filtered search: eligibility bitmap (one bit per row) for the filtered scan
     DevBuf<uint32_t> allow_bits;
+    DevBuf<float> scale_masked;          // the per-row scale with the filter folded in (filtered tcgen05 scan)
     PinBuf<uint32_t> h_allow_bits;
     // exhaustive fallback scratch
     DevBuf<uint32_t> fb_list, fb_count;
@@ -605,14 +606,20 @@ int gemv_pass(orx_index *ix, const float *q_src, int q0, int nq, int k, const Se
     for (int s = 0; s < nq; s += GEMV_QCHUNK) {
         const int m = std::min(GEMV_QCHUNK, nq - s);
         const int qa = q0 + s;
-        CK(ix->cur->partial.ensure((size_t)m * grid * 32 * slots));
+        // several queries: the batched kernel (8 queries share every row through shared memory); one: the streaming kernel
+        const int parts = m >= 2 ? orx::scan_gemv_batch_parts(ix->device, n_rows, m) : grid;
+        CK(ix->cur->partial.ensure((size_t)m * parts * 32 * slots));
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         if (e0 && e1) CK(cudaEventRecord(e0, ix->stream));
-        orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->cur->qhat.p + (size_t)qa * ORX_DIM, m,
-                              slots, ix->cur->partial.p, grid, ix->stream);
+        if (m >= 2)
+            orx::launch_scan_gemv_batch(ix->dtype, ix->table, ix->scale, n_rows, ix->cur->qhat.p + (size_t)qa * ORX_DIM, m,
+                                        slots, ix->cur->partial.p, parts, ix->stream);
+        else
+            orx::launch_scan_gemv(ix->dtype, ix->table, ix->scale, n_rows, ix->cur->qhat.p + (size_t)qa * ORX_DIM, m,
+                                  slots, ix->cur->partial.p, grid, ix->stream);
         if (e0 && e1) CK(cudaEventRecord(e1, ix->stream));
         orx::launch_finalize(ix->dtype, ix->table, ix->n2, ix->row_ids, q_src + (size_t)qa * ORX_DIM,
-                             ix->cur->prep.p + qa, ix->cur->partial.p, grid, slots, m, k, n_rows, eps, ctx.out, qa, ctx.pub,
+                             ix->cur->prep.p + qa, ix->cur->partial.p, parts, slots, m, k, n_rows, eps, ctx.out, qa, ctx.pub,
                              ctx.done, ix->stream);
         ix->stats.kernel_launches += 2;
     }
@@ -670,7 +677,7 @@ int stage_queries(orx_index *ix, const float *queries, int nq, const float **q_s
 // ---- the scan + finalize of all nq queries (tcgen05 for batches, GEMV otherwise); *path = 1 / 2
 int scan_pass(orx_index *ix, const float *q_src, int nq, int k, const SearchCtx &ctx, int *path) {
     const uint32_t n_rows = (uint32_t)ix->n_live;
-    if (ix->cur->umma && k <= 32 && orx::umma_should_use(ix->cur->umma, nq, n_rows)) {
+    if (ix->cur->umma && orx::umma_should_use(ix->cur->umma, nq, k, n_rows)) {
         *path = 2;
         cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
         int rc = orx::umma_search(ix->cur->umma, ix->dtype, ix->table, ix->scale, ix->n2, ix->row_ids, n_rows,
@@ -984,7 +991,35 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
         ix->stats.kernel_launches += m ? 2 : 1;
     };
     const int slots = orx::slots_for_k(k);
-    if (f.bits != nullptr && m > 32u * (uint32_t)slots) {
+    const uint32_t n_live = (uint32_t)ix->n_live;
+    // the unproven queries of either scan are re-answered exactly from the eligible list
+    auto redo_unproven = [&]() {
+        for (int j = 0; j < nq; ++j) {
+            if (!(ix->cur->h_flags.p[j] & 1) || (ix->cur->h_flags.p[j] & 2)) continue;
+            ix->stats.fallback_exhaustive += 1;
+            list_query(j);
+        }
+    };
+    if (f.bits != nullptr && m > 32u * (uint32_t)slots && ix->cur->umma &&
+        orx::umma_should_use(ix->cur->umma, nq, k, n_live) && (uint64_t)nq * m >= (uint64_t)n_live) {
+        // a BATCH of filtered queries whose bitmap scans together would read more than the whole table: ONE tcgen05 pass
+        // over all rows instead.  The predicate enters through the per-row scale (a cleared bit -> the "never a candidate"
+        // marker), so the kernel and its candidate proof are those of orx_search.
+        CK(ix->scale_masked.ensure(n_live));
+        orx::launch_mask_scale(ix->scale, f.bits, n_live, ix->scale_masked.p, st);
+        ix->stats.kernel_launches += 1;
+        ix->cur->scan_ev_used = 0;
+        cudaEvent_t e0 = scan_event(ix), e1 = scan_event(ix);
+        rc = orx::umma_search(ix->cur->umma, ix->dtype, ix->table, ix->scale_masked.p, ix->n2, ix->row_ids, n_live, q_src,
+                              ix->cur->qhat.p, ix->cur->qhat16.p, ix->cur->prep.p, nq, k, out, orx::PublishArgs{}, orx::DoneArgs{},
+                              st, &ix->stats.kernel_launches, e0, e1);
+        if (rc != ORX_OK) return fail(rc, "tcgen05 scan failed: %s", orx::umma_last_error());
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        harvest_scan_events(ix);
+        ix->stats.last_path = 2;
+        redo_unproven();
+    } else if (f.bits != nullptr && m > 32u * (uint32_t)slots) {
         // many eligible rows: the predicate is a row bitmap and the sequential scan skips the rows whose
         // bit is clear (HBM traffic = eligible rows only); same candidate proof as orx_search, the rare
         // unproven query is re-answered by the exact list path.
@@ -1009,11 +1044,7 @@ int filtered_search_locked(orx_index *ix, const FilterOnDevice &f, const float *
         CK(cudaGetLastError());
         harvest_scan_events(ix);
         ix->stats.last_path = 1;
-        for (int j = 0; j < nq; ++j) {
-            if (!(ix->cur->h_flags.p[j] & 1) || (ix->cur->h_flags.p[j] & 2)) continue;
-            ix->stats.fallback_exhaustive += 1;
-            list_query(j);
-        }
+        redo_unproven();
     } else {
         // few rows: no scan at all
         for (int j = 0; j < nq; ++j) list_query(j);
@@ -1293,12 +1324,10 @@ int set_error(int code, const char *fmt, ...) {
     g_err = buf;
     return code;
 }
-cudaStream_t index_stream(const orx_index *ix) {
+int index_device(const orx_index *ix) {
     if (ix->group) ix = ix->group->shards[0];          // a multi-GPU index stages on its first device
-    std::lock_guard<std::mutex> lk(ix->mu);
-    return ix->stream;
+    return ix->device;
 }
-int index_device(const orx_index *ix) { return ix->device; }
 void index_count_launches(orx_index *ix, uint64_t n) {
     if (ix->group) ix = ix->group->shards[0];
     std::lock_guard<std::mutex> lk(ix->mu);
@@ -1382,7 +1411,7 @@ void orx_destroy(orx_index *ix) {
     cudaFree(ix->n2);
     cudaFree(ix->row_ids);
     ix->fb_list.release(); ix->fb_count.release(); ix->fb_dist.release();
-    ix->allow_bits.release(); ix->h_allow_bits.release();
+    ix->allow_bits.release(); ix->h_allow_bits.release(); ix->scale_masked.release();
     ix->stage.release(); ix->d_src_idx.release(); ix->d_dst_row.release(); ix->d_ids.release();
     ix->d_flag.release(); ix->h_u32a.release(); ix->h_u32b.release(); ix->h_flag.release();
     if (ix->xchg) {

@@ -25,6 +25,9 @@
 #include <locale.h>
 #include <string>
 
+#include <string>
+#include <thread>
+
 #include "internal.h"
 
 namespace orx {
@@ -91,15 +94,29 @@ struct orx_pgcopy {
     int device = 0;                   // the index's GPU (kept here: freeing the loader must not touch the index)
     uint32_t world = 1, rank = 0;     // row-sharded load: keep only the ids this rank owns (sharded.py shard_of)
     enum State { HEADER, EXTENSION, TUPLES, DONE, FAILED } state = HEADER;
-    uint8_t *raw = nullptr;           // staging (pinned when loading): the bytes not yet flushed
+    // TWO batch buffer sets: while the GPU side of a full batch (H2D copy, decode, validate, commit, id map) runs on a
+    // helper thread, the caller's thread keeps copying and parsing the stream into the other set
+    struct Batch {
+        uint8_t *raw = nullptr;       // staging (pinned when loading)
+        orx_id *ids = nullptr;        // rows parsed inside raw[0, pos): id and payload offset
+        uint64_t *offs = nullptr;
+        uint8_t *d_raw = nullptr;
+        uint64_t *d_offs = nullptr;
+        float *d_vecs = nullptr;
+    } batch[2];
+    int cur = 0;
+    uint8_t *raw = nullptr;           // = batch[cur].raw: the bytes not yet flushed
     size_t fill = 0, pos = 0;         // bytes held / parsed
     uint64_t skip = 0;                // header extension bytes still to drop
-    orx_id *ids = nullptr;            // rows parsed inside raw[0, pos): id and payload offset
+    orx_id *ids = nullptr;            // = batch[cur].ids / offs
     uint64_t *offs = nullptr;
     uint32_t n_batch = 0;
-    uint8_t *d_raw = nullptr;
-    uint64_t *d_offs = nullptr;
-    float *d_vecs = nullptr;
+    cudaStream_t st = nullptr;        // the loader's own stream (copy + decode): several loaders may feed one index
+    std::thread job;                  // the batch in flight on the GPU side
+    bool job_running = false;
+    int job_rc = ORX_OK;
+    uint32_t job_rows = 0;
+    std::string job_err;
     uint64_t rows = 0, nulls = 0, foreign = 0, bytes = 0;
     int err = ORX_OK;
 };
@@ -113,22 +130,26 @@ int pg_fail(orx_pgcopy *ld, int code) {
 }
 
 void pg_free(orx_pgcopy *ld) {
+    if (ld->job.joinable()) ld->job.join();
     if (ld->ix) {
         int prev = -1;
         cudaGetDevice(&prev);
         cudaSetDevice(ld->device);
-        if (ld->raw) cudaFreeHost(ld->raw);
-        if (ld->ids) cudaFreeHost(ld->ids);
-        if (ld->offs) cudaFreeHost(ld->offs);
-        if (ld->d_raw) cudaFree(ld->d_raw);
-        if (ld->d_offs) cudaFree(ld->d_offs);
-        if (ld->d_vecs) cudaFree(ld->d_vecs);
+        for (orx_pgcopy::Batch &b : ld->batch) {
+            if (b.raw) cudaFreeHost(b.raw);
+            if (b.ids) cudaFreeHost(b.ids);
+            if (b.offs) cudaFreeHost(b.offs);
+            if (b.d_raw) cudaFree(b.d_raw);
+            if (b.d_offs) cudaFree(b.d_offs);
+            if (b.d_vecs) cudaFree(b.d_vecs);
+        }
+        if (ld->st) cudaStreamDestroy(ld->st);
         cudaGetLastError();
         if (prev >= 0) cudaSetDevice(prev);
     } else {
-        free(ld->raw);
-        free(ld->ids);
-        free(ld->offs);
+        free(ld->batch[0].raw);
+        free(ld->batch[0].ids);
+        free(ld->batch[0].offs);
     }
     delete ld;
 }
@@ -146,30 +167,67 @@ int pg_check_elements_host(orx_pgcopy *ld, const uint8_t *payload) {
     return ORX_OK;
 }
 
-// hand the rows parsed so far to the table; afterwards raw[0, pos) is dead
+// the GPU side of one full batch (runs on the helper thread): raw bytes -> HBM, decode, upsert
+void pg_job(orx_pgcopy *ld, orx_pgcopy::Batch *b, uint32_t n, size_t bytes) {
+    cudaSetDevice(ld->device);
+    cudaStream_t st = ld->st;
+    cudaError_t e = cudaMemcpyAsync(b->d_raw, b->raw, bytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_offs, b->offs, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        orx::launch_decode_pgvector(b->d_raw, b->d_offs, n, b->d_vecs, st);
+        orx::index_count_launches(ld->ix, 1);
+        e = cudaGetLastError();
+    }
+    // the rows are decoded on the loader's stream and committed on the index's: only this helper thread waits in between
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        ld->job_rc = ORX_ERR_CUDA;
+        ld->job_err = std::string("COPY decode failed: ") + cudaGetErrorString(e);
+        return;
+    }
+    const int rc = orx_upsert(ld->ix, b->ids, b->d_vecs, n, ORX_DIM);
+    ld->job_rc = rc;
+    if (rc != ORX_OK) ld->job_err = orx_last_error();
+}
+
+// wait for the batch in flight (if any) and account for it
+int pg_join(orx_pgcopy *ld) {
+    if (!ld->job_running) return ORX_OK;
+    ld->job.join();
+    ld->job_running = false;
+    if (ld->job_rc != ORX_OK) {
+        orx::set_error(ld->job_rc, "%s", ld->job_err.c_str());
+        return pg_fail(ld, ld->job_rc);
+    }
+    ld->rows += ld->job_rows;
+    return ORX_OK;
+}
+
+// hand the rows parsed so far to the table; afterwards raw[0, pos) is dead.  The batch is loaded by the helper thread
+// while the caller goes on parsing into the other buffer set; its outcome is collected by the NEXT flush (or the close).
 int pg_flush(orx_pgcopy *ld) {
     const uint32_t n = ld->n_batch;
-    if (n && ld->ix) {
-        int prev = -1;
-        cudaGetDevice(&prev);
-        const int dev = ld->device;
-        if (prev != dev) cudaSetDevice(dev);
-        cudaStream_t st = orx::index_stream(ld->ix);
-        cudaError_t e = cudaMemcpyAsync(ld->d_raw, ld->raw, ld->pos, cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(ld->d_offs, ld->offs, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess) {
-            orx::launch_decode_pgvector(ld->d_raw, ld->d_offs, n, ld->d_vecs, st);
-            orx::index_count_launches(ld->ix, 1);
-            e = cudaGetLastError();
+    if (ld->ix) {
+        int rc = pg_join(ld);                       // at most one batch in flight: the other buffer set is free now
+        if (rc != ORX_OK) return rc;
+        orx_pgcopy::Batch *b = &ld->batch[ld->cur];
+        const size_t done = ld->pos, left = ld->fill - ld->pos;
+        ld->cur ^= 1;
+        orx_pgcopy::Batch *nb = &ld->batch[ld->cur];
+        memcpy(nb->raw, b->raw + done, left);       // the unparsed tail moves to the other set
+        ld->raw = nb->raw;
+        ld->ids = nb->ids;
+        ld->offs = nb->offs;
+        ld->fill = left;
+        ld->pos = 0;
+        ld->n_batch = 0;
+        if (n) {
+            ld->job_rc = ORX_OK;
+            ld->job_rows = n;
+            ld->job_running = true;
+            ld->job = std::thread(pg_job, ld, b, n, done);
         }
-        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
-        if (e != cudaSuccess) {
-            orx::set_error(ORX_ERR_CUDA, "COPY decode failed: %s", cudaGetErrorString(e));
-            return pg_fail(ld, ORX_ERR_CUDA);
-        }
-        // same stream: the upsert reads the decoded rows after the kernel, and synchronises before it returns
-        const int rc = orx_upsert(ld->ix, ld->ids, ld->d_vecs, n, ORX_DIM);
-        if (rc != ORX_OK) return pg_fail(ld, rc);
+        return ORX_OK;
     }
     ld->rows += n;
     ld->n_batch = 0;
@@ -334,12 +392,18 @@ int orx_pgcopy_open_sharded(orx_index *ix, int world, int rank, orx_pgcopy **out
         cudaGetDevice(&prev);
         ld->device = orx::index_device(ix);
         cudaSetDevice(ld->device);
-        cudaError_t e = cudaHostAlloc(reinterpret_cast<void **>(&ld->raw), PG_RAW_CAP, cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&ld->ids), PG_BATCH_ROWS * sizeof(orx_id), cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&ld->offs), PG_BATCH_ROWS * sizeof(uint64_t), cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ld->d_raw), PG_RAW_CAP + 16);
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ld->d_offs), PG_BATCH_ROWS * sizeof(uint64_t));
-        if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&ld->d_vecs), (size_t)PG_BATCH_ROWS * ORX_DIM * sizeof(float));
+        cudaError_t e = cudaStreamCreateWithFlags(&ld->st, cudaStreamNonBlocking);
+        for (orx_pgcopy::Batch &b : ld->batch) {
+            if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&b.raw), PG_RAW_CAP, cudaHostAllocPortable);
+            if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&b.ids), PG_BATCH_ROWS * sizeof(orx_id), cudaHostAllocPortable);
+            if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void **>(&b.offs), PG_BATCH_ROWS * sizeof(uint64_t), cudaHostAllocPortable);
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&b.d_raw), PG_RAW_CAP + 16);
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&b.d_offs), PG_BATCH_ROWS * sizeof(uint64_t));
+            if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&b.d_vecs), (size_t)PG_BATCH_ROWS * ORX_DIM * sizeof(float));
+        }
+        ld->raw = ld->batch[0].raw;
+        ld->ids = ld->batch[0].ids;
+        ld->offs = ld->batch[0].offs;
         if (prev >= 0) cudaSetDevice(prev);
         if (e != cudaSuccess) {
             cudaGetLastError();
@@ -347,9 +411,9 @@ int orx_pgcopy_open_sharded(orx_index *ix, int world, int rank, orx_pgcopy **out
             return orx::set_error(ORX_ERR_CUDA, "COPY loader buffers: %s", cudaGetErrorString(e));
         }
     } else {
-        ld->raw = static_cast<uint8_t *>(malloc(PG_RAW_CAP));
-        ld->ids = static_cast<orx_id *>(malloc(PG_BATCH_ROWS * sizeof(orx_id)));
-        ld->offs = static_cast<uint64_t *>(malloc(PG_BATCH_ROWS * sizeof(uint64_t)));
+        ld->raw = ld->batch[0].raw = static_cast<uint8_t *>(malloc(PG_RAW_CAP));
+        ld->ids = ld->batch[0].ids = static_cast<orx_id *>(malloc(PG_BATCH_ROWS * sizeof(orx_id)));
+        ld->offs = ld->batch[0].offs = static_cast<uint64_t *>(malloc(PG_BATCH_ROWS * sizeof(uint64_t)));
         if (!ld->raw || !ld->ids || !ld->offs) {
             pg_free(ld);
             return orx::set_error(ORX_ERR_INVALID, "COPY loader buffers: out of host memory");
@@ -384,6 +448,7 @@ int orx_pgcopy_close(orx_pgcopy *ld, uint64_t *rows_loaded, uint64_t *rows_null)
     int rc = ld->err;
     if (ld->state != orx_pgcopy::FAILED) {
         rc = pg_drain(ld, true);
+        if (rc == ORX_OK) rc = pg_join(ld);          // the last batch has landed (or failed)
         // EOF at a tuple boundary ends the data like the -1 marker does (Postgres' CopyFrom treats it so);
         // anything else is a truncated stream.  Rows of batches flushed earlier stay loaded, like the
         // batches a COPY consumer already committed.

@@ -99,6 +99,82 @@ scan_gemv_kernel(const T *__restrict__ table, const float *__restrict__ scale, u
     cta_merge_store<S>(top, s_keys, partial, lane, warp);
 }
 
+// ------------------------------------------------------------------ batched exact scan
+// The same fp32 scan for a BATCH the tensor-core pass cannot take (k beyond its candidate lists): the 8 warps of a CTA
+// serve 8 DIFFERENT queries and share every row through shared memory, so a row is fetched once per 8 queries instead
+// of once per query (cp.async 16-byte copies, double-buffered tiles of 16 KB).  Each warp keeps its query slice in
+// registers and scores a row with the SAME instruction sequence as the single-query scan (warp_row_dot on the same
+// lane / vector assignment), so fast scores, error bound and completeness proof are those of scan_gemv_kernel; a warp's
+// sorted top-K is the (query, CTA) list itself.  grid = (row partitions, ceil(nq / 8)); CTAs that differ only in their
+// query group walk the same tiles at the same time, so the extra passes are served by L2.
+template <typename T> struct BatchTile { static constexpr int ROWS = sizeof(T) == 4 ? 4 : 8; };     // 16 KB of rows
+
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+                 : "memory");
+}
+
+template <typename T, int S>
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
+scan_gemv_batch_kernel(const T *__restrict__ table, const float *__restrict__ scale, uint32_t n_rows,
+                       const float *__restrict__ qhat_all, int nq, uint64_t *__restrict__ partial_all) {
+    constexpr int NV = RowVec<T>::NV;
+    constexpr int VPR = RowVec<T>::VEC_PER_ROW;
+    constexpr int ROWS = BatchTile<T>::ROWS;
+    constexpr int TILE_VECS = ROWS * VPR;                      // 1024 16-byte vectors
+    constexpr int K = 32 * S;
+    __shared__ uint4 s_rows[2][TILE_VECS];
+
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int query = blockIdx.y * SCAN_WARPS + warp;
+    const bool active = query < nq;
+
+    pdl_launch_dependents();
+    pdl_wait();
+    float4 qv[8];
+    load_q_slice<T>(qhat_all + (size_t)(active ? query : 0) * ORX_DIM, lane, qv);
+
+    WarpTopK<S> top;
+    top.init();
+
+    const uint4 *tab = reinterpret_cast<const uint4 *>(table);
+    const uint32_t n_tiles = (n_rows + ROWS - 1) / ROWS;
+    auto fetch = [&](uint32_t t, int buf) {
+#pragma unroll
+        for (int i = 0; i < TILE_VECS / SCAN_THREADS; ++i) {
+            const int idx = threadIdx.x + i * SCAN_THREADS;
+            const uint32_t row = min(t * ROWS + (uint32_t)(idx / VPR), n_rows - 1);      // tail rows re-read the last row
+            cp_async_16(&s_rows[buf][idx], tab + (size_t)row * VPR + (idx % VPR));
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t t = blockIdx.x;
+    int buf = 0;
+    if (t < n_tiles) fetch(t, 0);
+    for (; t < n_tiles; t += gridDim.x, buf ^= 1) {
+        const uint32_t t_next = t + gridDim.x;
+        if (t_next < n_tiles) {
+            fetch(t_next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();                                       // every thread's copies of this tile have landed
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            uint4 v[NV];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) v[j] = s_rows[buf][r * VPR + lane + 32 * j];
+            const float acc = warp_row_dot<T>(v, qv);
+            const uint32_t row = t * ROWS + r;
+            if (active && row < n_rows) top.offer(make_key(score_ord(acc, __ldg(scale + row)), row), lane);
+        }
+        __syncthreads();                                       // the buffer may be refilled by the next iteration
+    }
+    if (active) top.store(partial_all + ((size_t)query * gridDim.x + blockIdx.x) * K, lane);
+}
+
 // ------------------------------------------------------------------ filtered scan
 // The same scan restricted to the rows whose bit is set in `allow_bits` (bit r%32 of word r/32; bits at
 // or beyond n_rows are 0): the SQL with a WHERE clause once the predicate is resolved to rows
@@ -195,6 +271,38 @@ void launch_scan_gemv(int dtype, const void *table, const float *scale, uint32_t
         launch_scan_gemv_t<float>(table, scale, n_rows, qhat, nq, slots, partial, grid, st);
     else
         launch_scan_gemv_t<__nv_bfloat16>(table, scale, n_rows, qhat, nq, slots, partial, grid, st);
+}
+
+// partitions of the batched scan: two resident CTAs per SM over all query groups, at least one tile each
+int scan_gemv_batch_parts(int device, uint32_t n_rows, int nq) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 1;
+    const int groups = (nq + SCAN_WARPS - 1) / SCAN_WARPS;
+    int parts = (2 * sms + groups - 1) / groups;
+    const uint32_t tiles = (n_rows + 3) / 4;
+    if ((uint32_t)parts > tiles) parts = (int)tiles;
+    return parts < 1 ? 1 : parts;
+}
+
+template <typename T>
+static void launch_scan_gemv_batch_t(const void *table, const float *scale, uint32_t n_rows, const float *qhat, int nq,
+                                     int slots, uint64_t *partial, int parts, cudaStream_t st) {
+    dim3 g(parts, (nq + SCAN_WARPS - 1) / SCAN_WARPS);
+    const T *tab = static_cast<const T *>(table);
+    switch (slots) {
+        case 1: launch_pdl(scan_gemv_batch_kernel<T, 1>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, nq, partial); break;
+        case 2: launch_pdl(scan_gemv_batch_kernel<T, 2>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, nq, partial); break;
+        case 4: launch_pdl(scan_gemv_batch_kernel<T, 4>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, nq, partial); break;
+        default: launch_pdl(scan_gemv_batch_kernel<T, 5>, g, dim3(SCAN_THREADS), 0, st, tab, scale, n_rows, qhat, nq, partial); break;
+    }
+}
+
+void launch_scan_gemv_batch(int dtype, const void *table, const float *scale, uint32_t n_rows, const float *qhat, int nq,
+                            int slots, uint64_t *partial, int parts, cudaStream_t st) {
+    if (dtype == ORX_DTYPE_F32)
+        launch_scan_gemv_batch_t<float>(table, scale, n_rows, qhat, nq, slots, partial, parts, st);
+    else
+        launch_scan_gemv_batch_t<__nv_bfloat16>(table, scale, n_rows, qhat, nq, slots, partial, parts, st);
 }
 
 template <typename T>

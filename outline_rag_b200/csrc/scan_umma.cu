@@ -50,7 +50,13 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = TILE_M * 128;  // 16 KB: 128 rows x one 128-byte swizzle row of K
 constexpr int B_BYTES = TILE_N * 128;  // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int CAND = 64;               // candidate slots per (query, CTA) = finalize S=2 list
+// Candidate slots per (query, CTA).  A list must hold the CTA's k best coarse scores AND every row within the margin
+// (2 eps + 1e-6 = 5e-3) below the k-th of them; measured on the synthetic corpus (tools/bench_wide_k.py) that is ~2.2-2.5 k
+// rows, so: 64 keys (finalize S=2) up to k = 16, 160 keys (S=5) up to k = 64.  Beyond that even finalize's 160 rescored
+// candidates cannot prove a tf32 / bf16 coarse ranking, and the caller keeps the exact fp32 scan (UMMA_MAX_K, scan_umma.h).
+constexpr int CAND = 64;
+constexpr int CAND_WIDE = 160;
+constexpr int CAND_NARROW_MAX_K = 16;
 constexpr int SMEM_MAIN = STAGES * STAGE_BYTES;
 constexpr int SMEM_SCALE = 2 * TILE_N * 4;
 constexpr int SMEM_TOTAL = SMEM_MAIN + SMEM_SCALE + 256 + 1024;   // + barriers + alignment slack
@@ -242,40 +248,60 @@ __host__ __device__ constexpr uint32_t make_idesc(bool tf32, int m = TILE_M) {
 }
 
 // ------------------------------------------------------------------ candidate list upkeep
-// Warp-cooperative compaction of lane L's candidate list (<= 64 keys, two per lane): raise L's
+// Warp-cooperative compaction of lane L's candidate list (<= 32 x CPL keys, CPL per lane): raise L's
 // threshold to (k-th best REGULAR coarse score) - margin, keep what is still above it (and every
 // ORD_ALWAYS key), publish the threshold.  All 32 lanes call this with the same L.
+template <int CPL>
 __device__ __forceinline__ void coop_compact(uint64_t *list, int L, int lane, int &cnt, float &thr, int k,
                                              float margin, uint32_t *gthr_L) {
     __syncwarp();                                    // lane L's appends are visible to the warp
     const int n = __shfl_sync(FULL_MASK, cnt, L);
     const float thr_L = __shfl_sync(FULL_MASK, thr, L);
-    const uint64_t k0 = lane < n ? list[lane] : 0ull;
-    const uint64_t k1 = lane + 32 < n ? list[lane + 32] : 0ull;
-    const bool a0 = key_ord(k0) == ORD_ALWAYS, a1 = key_ord(k1) == ORD_ALWAYS;
-    const uint64_t r0 = a0 ? 0ull : k0, r1 = a1 ? 0ull : k1;       // regular keys only take part in the ranking
-    int rank0 = 0, rank1 = 0;
-#pragma unroll 8
+    uint64_t key[CPL], reg[CPL];                     // reg: regular keys only take part in the ranking
+    bool alw[CPL];
+    int rank[CPL];
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        key[i] = lane + 32 * i < n ? list[lane + 32 * i] : 0ull;
+        alw[i] = key_ord(key[i]) == ORD_ALWAYS;
+        reg[i] = alw[i] ? 0ull : key[i];
+        rank[i] = 0;
+    }
+#pragma unroll 4
     for (int s = 0; s < 32; ++s) {
-        const uint64_t x = shfl_u64(r0, s), y = shfl_u64(r1, s);
-        rank0 += (x > r0) + (y > r0);
-        rank1 += (x > r1) + (y > r1);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            const uint64_t x = shfl_u64(reg[j], s);
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) rank[i] += (x > reg[i]);
+        }
     }
     // keys are unique (distinct rows), so exactly one regular key has rank k-1 when >= k exist
-    const uint32_t mine = (r0 != 0ull && rank0 == k - 1) ? key_ord(r0) : ((r1 != 0ull && rank1 == k - 1) ? key_ord(r1) : 0u);
+    uint32_t mine = 0u;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+        if (reg[i] != 0ull && rank[i] == k - 1) mine = key_ord(reg[i]);
     const uint32_t kth = __reduce_max_sync(FULL_MASK, mine);
     float new_thr = thr_L;
     if (kth != 0u) new_thr = fmaxf(thr_L, ord_to_float(kth) - margin);
-    const bool keep0 = k0 != 0ull && (a0 || ord_to_float(key_ord(k0)) > new_thr);
-    const bool keep1 = k1 != 0ull && (a1 || ord_to_float(key_ord(k1)) > new_thr);
-    const unsigned b0 = __ballot_sync(FULL_MASK, keep0), b1 = __ballot_sync(FULL_MASK, keep1);
     const unsigned lt = (1u << lane) - 1u;
+    bool keep[CPL];
+    int pos[CPL];
+    int total = 0;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        keep[i] = key[i] != 0ull && (alw[i] || ord_to_float(key_ord(key[i])) > new_thr);
+        const unsigned b = __ballot_sync(FULL_MASK, keep[i]);
+        pos[i] = total + __popc(b & lt);
+        total += __popc(b);
+    }
     __syncwarp();
-    if (keep0) list[__popc(b0 & lt)] = k0;
-    if (keep1) list[__popc(b0) + __popc(b1 & lt)] = k1;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+        if (keep[i]) list[pos[i]] = key[i];
     __syncwarp();
     if (lane == L) {
-        cnt = __popc(b0) + __popc(b1);
+        cnt = total;
         thr = new_thr;
         if (kth != 0u) atomicMax(gthr_L, float_to_ord(new_thr));
     }
@@ -286,7 +312,7 @@ __device__ __forceinline__ void coop_compact(uint64_t *list, int L, int lane, in
 // header.  `arrive_empty(buf)` hands accumulator buffer `buf` back to the MMA issuer.
 // DUMP (diagnostic instantiation behind orx_debug_coarse_scores): instead of selecting, every scaled coarse score is
 // written to dump[row * dump_ld + query], so that a test can MEASURE max |coarse - cosine| against eps.
-template <bool DUMP, class ArriveEmpty>
+template <bool DUMP, int C, class ArriveEmpty>
 __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int n_slots, uint32_t n_tiles,
                                               const float *__restrict__ scale, uint32_t n_rows, int k, float margin,
                                               uint64_t *__restrict__ partial, float *__restrict__ floor_out,
@@ -297,7 +323,7 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
     const int et = ew * 32 + lane;                          // 0..127
     const int q = q_base + ew * 32 + lane;
     const bool active = q < nq;
-    uint64_t *buf_keys = partial + ((size_t)(active ? q : 0) * n_slots + slot) * CAND;
+    uint64_t *buf_keys = partial + ((size_t)(active ? q : 0) * n_slots + slot) * C;
     uint32_t *gthr = gthr_all + (active ? q : 0);
     float thr = __int_as_float(0xff800000);                 // -inf
     int cnt = 0;
@@ -318,7 +344,9 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const float s = sc_next[h];
-            special |= !(fabsf(s) < __int_as_float(0x7f800000));      // inf or NaN
+            // +inf (irregular magnitude: always a candidate) needs the slow path; NaN (zero-norm row, row beyond the end, row
+            // excluded by a filter) needs nothing: its score is NaN, which fmaxf ignores and `> thr` rejects
+            special |= fabsf(s) == __int_as_float(0x7f800000);
             sts_f32(sc + 4 * (et + 128 * h), s);
             const uint32_t rn = n0 + (uint32_t)n_slots * TILE_N + et + 128 * h;
             sc_next[h] = (t + n_slots < n_tiles && rn < n_rows) ? __ldg(scale + rn) : __int_as_float(0x7fc00000);
@@ -382,7 +410,7 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
                     for (int j = 0; j < 32; ++j) mask |= (s[j] > thr) ? (1u << j) : 0u;
                     mask = (mask & ~always) | (overflow ? 0u : always);
                 }
-                const unsigned need = __ballot_sync(FULL_MASK, active && cnt + __popc(mask) > CAND);
+                const unsigned need = __ballot_sync(FULL_MASK, active && cnt + __popc(mask) > C);
                 if (!need) break;
                 if (round == 1) {
                     // near-ties wider than the list: the query is re-answered by the fp32 scan
@@ -397,8 +425,8 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
                 while (todo) {
                     const int L = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    uint64_t *list_L = partial + ((size_t)(q - lane + L) * n_slots + slot) * CAND;
-                    coop_compact(list_L, L, lane, cnt, thr, k, margin, gthr_all + (q - lane + L));
+                    uint64_t *list_L = partial + ((size_t)(q - lane + L) * n_slots + slot) * C;
+                    coop_compact<C / 32>(list_L, L, lane, cnt, thr, k, margin, gthr_all + (q - lane + L));
                 }
             }
             if (mask) {
@@ -415,12 +443,12 @@ __device__ __forceinline__ void epilogue_loop(int q_base, int nq, int slot, int 
         if (++buf == 2) { buf = 0; tphase ^= 1; }
     }
     if (active && !DUMP) {
-        for (int i = cnt; i < CAND; ++i) buf_keys[i] = 0ull;
+        for (int i = cnt; i < C; ++i) buf_keys[i] = 0ull;
         floor_out[(size_t)q * n_slots + slot] = overflow ? __int_as_float(0x7f800000) : thr;
     }
 }
 
-template <bool TF32, bool DUMP = false>
+template <bool TF32, bool DUMP = false, int C = CAND>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                  const float *__restrict__ scale, uint32_t n_rows, int nq, int m_tiles, int n_slots, int k,
@@ -515,7 +543,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
         }
     } else if (warp < 4) {
         // ========================================================================= epilogue
-        epilogue_loop<DUMP>(m_tile * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin, partial, floor_out,
+        epilogue_loop<DUMP, C>(m_tile * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin, partial, floor_out,
                             gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
                             [&](uint32_t b) { mbar_arrive(bar_tempty + 8 * b); }, dump, dump_ld ORX_DBG_FWD);
     }
@@ -536,7 +564,7 @@ scan_umma_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constan
 // ring (3072 MMA cycles of prefetch instead of 2048).  Only the leader CTA issues MMAs; commits are
 // multicast to both CTAs' barriers; both CTAs' TMA bytes are counted on the leader's full barrier;
 // both CTAs' epilogues hand accumulators back by arriving on the leader's tmem-empty barrier.
-template <bool TF32, bool DUMP = false>
+template <bool TF32, bool DUMP = false, int C = CAND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UM_THREADS, 1)
 scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x,
                   const float *__restrict__ scale, uint32_t n_rows, int nq, int m_pairs, int n_slots, int k,
@@ -639,7 +667,7 @@ scan_umma2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     } else if (warp < 4) {
         // ============================================== epilogue (each CTA: its own 128 queries)
         const uint32_t tempty_leader = map_to_cta(bar_tempty, 0);
-        epilogue_loop<DUMP>(m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
+        epilogue_loop<DUMP, C>(m_pair * 2 * TILE_M + (int)cta_rank * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
                             partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
                             [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); }, dump, dump_ld ORX_DBG_FWD);
     }
@@ -780,7 +808,7 @@ scan_umma2r_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     } else if (warp < 4) {
         // ============================================== epilogue (each CTA: its own 128 queries)
         const uint32_t tempty_leader = map_to_cta(bar_tempty, 0);
-        epilogue_loop<false>(q_row, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
+        epilogue_loop<false, CAND>(q_row, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
                              partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
                              [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); }, nullptr, 0u
 #ifdef ORX_DEBUG_VARIANTS
@@ -910,7 +938,7 @@ scan_umma4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_consta
     } else if (warp < 4) {
         // ============================================== epilogue (each CTA: its own 128 queries)
         const uint32_t tempty_leader = map_to_cta(bar_tempty, leader_rank);
-        epilogue_loop<false>(m_pair * 2 * TILE_M + (int)parity * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
+        epilogue_loop<false, CAND>(m_pair * 2 * TILE_M + (int)parity * TILE_M, nq, slot, n_slots, n_tiles, scale, n_rows, k, margin,
                              partial, floor_out, gthr_all, s_scale, bar_tfull, tmem_base, warp, lane,
                              [&](uint32_t b) { mbar_arrive_cluster(tempty_leader + 8 * b); }, nullptr, 0u
 #ifdef ORX_DEBUG_VARIANTS
@@ -1017,9 +1045,9 @@ void umma_plan_destroy(UmmaPlan *p) {
 void umma_plan_invalidate(UmmaPlan *) {}      // tensor maps are encoded per search (pointer + live row count)
 const char *umma_last_error() { return g_umma_err.c_str(); }
 
-bool umma_should_use(const UmmaPlan *p, int nq, uint32_t n_rows) {
+bool umma_should_use(const UmmaPlan *p, int nq, int k, uint32_t n_rows) {
     // one table pass for the whole batch beats nq GEMV passes as soon as nq >= 2
-    return p != nullptr && nq >= 2 && n_rows >= 4096;     // (k <= 32 is checked by the caller: 64-slot lists)
+    return p != nullptr && nq >= 2 && k <= UMMA_MAX_K && n_rows >= 4096;
 }
 
 static bool ensure_attrs(UmmaPlan *p) {
@@ -1036,6 +1064,10 @@ static bool ensure_attrs(UmmaPlan *p) {
     set((const void *)scan_umma2_kernel<false, false>, SMEM2_TOTAL);
     set((const void *)scan_umma2_kernel<true, true>, SMEM2_TOTAL);
     set((const void *)scan_umma2_kernel<false, true>, SMEM2_TOTAL);
+    set((const void *)scan_umma_kernel<true, false, CAND_WIDE>, SMEM_TOTAL);
+    set((const void *)scan_umma_kernel<false, false, CAND_WIDE>, SMEM_TOTAL);
+    set((const void *)scan_umma2_kernel<true, false, CAND_WIDE>, SMEM2_TOTAL);
+    set((const void *)scan_umma2_kernel<false, false, CAND_WIDE>, SMEM2_TOTAL);
     set((const void *)scan_umma2r_kernel, SMEM2R_TOTAL);
     set((const void *)scan_umma4_kernel<true>, SMEM2_TOTAL);
     set((const void *)scan_umma4_kernel<false>, SMEM2_TOTAL);
@@ -1093,6 +1125,9 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
     const double eps = tf32 ? EPS_UMMA_TF32 : EPS_UMMA_BF16;
     const float margin = (float)(2.0 * eps + 1e-6);
     if (!ensure_attrs(p)) return ORX_ERR_CUDA;
+    if (k > UMMA_MAX_K) { g_umma_err = "k beyond the candidate lists"; return ORX_ERR_INVALID; }
+    const bool wide = k > CAND_NARROW_MAX_K;   // lists of 160 instead of 64 keys per (query, CTA)
+    const int cand = wide ? CAND_WIDE : CAND;
     constexpr int MAX_Q = 2048;              // 16 query tiles -> 9 row slots -> 144 CTAs
     for (int q0 = 0; q0 < nq; q0 += MAX_Q) {
         const int m = nq - q0 < MAX_Q ? nq - q0 : MAX_Q;
@@ -1102,12 +1137,12 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
         const uint32_t n_tiles = (n_rows + TILE_N - 1) / TILE_N;
         // clusters of 4 (two pairs sharing the table tile by multicast) when the batch has an even number of pair tiles
         int quads_fit = 0;
-        if (pairs && p->use_quads && m_tiles % 2 == 0) quads_fit = max_active_quads(p, tf32) / (m_tiles / 2);
+        if (pairs && p->use_quads && !wide && m_tiles % 2 == 0) quads_fit = max_active_quads(p, tf32) / (m_tiles / 2);
         const bool quads = quads_fit >= 1;
         int n_slots = quads ? quads_fit : (pairs ? p->sms / 2 : p->sms) / m_tiles;
         if (n_slots < 1) n_slots = 1;
         if ((uint32_t)n_slots > n_tiles) n_slots = (int)n_tiles;
-        cudaError_t e = ensure_buf(p->partial, p->partial_n, (size_t)m * n_slots * CAND);
+        cudaError_t e = ensure_buf(p->partial, p->partial_n, (size_t)m * n_slots * cand);
         if (e == cudaSuccess) e = ensure_buf(p->floor, p->floor_n, (size_t)m * n_slots);
         if (e == cudaSuccess) e = ensure_buf(p->gthr, p->gthr_n, (size_t)m);
         if (e != cudaSuccess) { g_umma_err = cudaGetErrorString(e); return ORX_ERR_CUDA; }
@@ -1126,29 +1161,33 @@ int umma_search(UmmaPlan *p, int dtype, const void *table, const float *scale, c
             else
                 scan_umma4_kernel<false><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles / 2, n_slots,
                                                                                 k, margin, p->partial, p->floor, p->gthr);
-        } else if (pairs && !tf32 && p->use_ares) {
+        } else if (pairs && !tf32 && p->use_ares && !wide) {
             const int grid = 2 * m_tiles * n_slots;
             scan_umma2r_kernel<<<grid, UM_THREADS, SMEM2R_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots, k, margin,
                                                                        p->partial, p->floor, p->gthr);
         } else if (pairs) {
             const int grid = 2 * m_tiles * n_slots;
-            if (tf32)
-                scan_umma2_kernel<true><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                               k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
-            else
-                scan_umma2_kernel<false><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                                k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
+#define ORX_LAUNCH_UMMA2(TF, C)                                                                                           \
+    scan_umma2_kernel<TF, false, C><<<grid, UM_THREADS, SMEM2_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots, k, \
+                                                                           margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p))
+            if (tf32 && wide) ORX_LAUNCH_UMMA2(true, CAND_WIDE);
+            else if (tf32) ORX_LAUNCH_UMMA2(true, CAND);
+            else if (wide) ORX_LAUNCH_UMMA2(false, CAND_WIDE);
+            else ORX_LAUNCH_UMMA2(false, CAND);
+#undef ORX_LAUNCH_UMMA2
         } else {
             const int grid = m_tiles * n_slots;
-            if (tf32)
-                scan_umma_kernel<true><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                             k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
-            else
-                scan_umma_kernel<false><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots,
-                                                                              k, margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p));
+#define ORX_LAUNCH_UMMA1(TF, C)                                                                                          \
+    scan_umma_kernel<TF, false, C><<<grid, UM_THREADS, SMEM_TOTAL, st>>>(map_q, map_x, scale, n_rows, m, m_tiles, n_slots, k,  \
+                                                                         margin, p->partial, p->floor, p->gthr, nullptr, 0u ORX_DBG_ARG(p))
+            if (tf32 && wide) ORX_LAUNCH_UMMA1(true, CAND_WIDE);
+            else if (tf32) ORX_LAUNCH_UMMA1(true, CAND);
+            else if (wide) ORX_LAUNCH_UMMA1(false, CAND_WIDE);
+            else ORX_LAUNCH_UMMA1(false, CAND);
+#undef ORX_LAUNCH_UMMA1
         }
         if (ev_end && q0 + MAX_Q >= nq) cudaEventRecord(ev_end, st);
-        launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, 2, m,
+        launch_finalize(dtype, table, n2, row_ids, q_dev + (size_t)q0 * ORX_DIM, prep + q0, p->partial, n_slots, cand / 32, m,
                         k, n_rows, eps, out, q0, pub, done, st, p->floor);
 #ifdef ORX_DEBUG_VARIANTS
         if (p->dbg && out.flags) launch_flags_from_prep(prep + q0, m, out.flags + q0, st);   // timing experiments: no fallbacks

@@ -209,4 +209,20 @@ void launch_gather_rows(int dtype, const void *table, const uint32_t *rows, uint
             static_cast<const __nv_bfloat16 *>(table), rows, n, out);
 }
 
+// ---- filtered tcgen05 scan: the row predicate enters the scan through the per-row scale -- a row whose bit is clear gets
+//      the "never a candidate" marker (NaN, the same as a zero-norm row), so the tensor-core epilogue needs no bitmap
+__global__ void mask_scale_kernel(const float *__restrict__ scale, const uint32_t *__restrict__ allow_bits, uint32_t n_rows,
+                                  float *__restrict__ out) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += stride) {
+        const uint32_t w = __ldg(allow_bits + (r >> 5));
+        out[r] = (w >> (r & 31)) & 1u ? scale[r] : __int_as_float(0x7fc00000);
+    }
+}
+void launch_mask_scale(const float *scale, const uint32_t *allow_bits, uint32_t n_rows, float *out, cudaStream_t st) {
+    if (n_rows == 0) return;
+    const uint32_t blocks = cap_grid((n_rows + 255u) / 256u, 8);
+    mask_scale_kernel<<<blocks, 256, 0, st>>>(scale, allow_bits, n_rows, out);
+}
+
 }  // namespace orx

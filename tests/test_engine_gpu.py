@@ -685,6 +685,66 @@ def test_filtered_search_with_many_eligible_rows_scans_through_a_row_bitmap(Inde
             assert np.array_equal(g_ids[i], w_ids) and np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64))
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_filtered_batches_take_one_tensor_core_pass(Index, synth100k, dtype):
+    """A batch of filtered queries whose bitmap scans would together read more than the table runs ONE tcgen05 pass: the
+    predicate is folded into the per-row scale (a cleared bit = the never-a-candidate marker).  Same answers as the oracle
+    on the eligible subset -- ids and distance bits -- for one query tile and for CTA pairs; batches too small for the
+    pass to pay keep the bitmap GEMV scan."""
+    n = 20_000
+    X = synth100k.table(n).copy()
+    Q, _ = synth100k.queries(200, n)
+    X[4000] = 0.0                                              # eligible zero-norm row
+    X[4001] = 0.0                                              # excluded zero-norm row
+    X[100:140] = X[99]                                         # 41 identical eligible rows
+    X[7000:7100] = X[6999]                                     # 101 identical rows, NOT eligible: must not flood anything
+    X[300] *= 1e30                                             # irregular magnitude ("always a candidate"), eligible
+    X[301] *= 1e30                                             # the same, excluded
+    ids = _ids(n, 1000)
+    rows = X if dtype == "fp32" else stored_bf16_rows(X)
+    rng = np.random.default_rng(5)
+    excluded = np.concatenate([[4001, 301], np.arange(6999, 7100)])
+    with Index(dtype) as ix:
+        ix.upsert(ids, X)
+        for m in (4500, 15_000):
+            sel = rng.choice(n, size=m, replace=False)
+            sel = np.setdiff1d(np.union1d(sel, np.concatenate([np.arange(99, 140), [4000, 300]])), excluded)
+            queries = np.concatenate([Q, X[99:100], X[6999:7000], np.zeros((1, DIM), np.float32)])
+            for nq in (9, len(queries)):
+                qs = queries[-nq:]
+                g_ids, g_d, g_c = ix.search_filtered(qs, K, ids[rng.permutation(sel)])
+                assert ix.stats()["last_path"] == 2, (m, nq)
+                for i in range(nq):
+                    w_ids, w_d = O.topk_exact(rows[sel], ids[sel], qs[i], K, exhaustive=True)
+                    assert g_c[i] == K
+                    assert np.array_equal(g_ids[i], w_ids), (m, nq, i)
+                    nan = np.isnan(w_d)
+                    assert np.array_equal(np.isnan(g_d[i]), nan), (m, nq, i)
+                    assert np.array_equal(g_d[i][~nan].view(np.uint64), w_d[~nan].view(np.uint64)), (m, nq, i)
+            # the same filter: a short batch (bitmap GEMV scan unless 2 x eligible >= rows), a wide k
+            a = ix.search_filtered(queries[:2], K, ids[sel])
+            assert ix.stats()["last_path"] == (2 if 2 * len(sel) >= n else 1)
+            b = ix.search_filtered(queries[:9], K, ids[sel])
+            assert ix.stats()["last_path"] == (2 if 9 * len(sel) >= n else 1)
+            assert np.array_equal(a[0], b[0][:2]) and np.array_equal(a[1].view(np.uint64), b[1][:2].view(np.uint64))
+            w = ix.search_filtered(queries[:9], 40, ids[sel])                   # k > 32: the 160-key candidate lists
+            assert ix.stats()["last_path"] == (2 if 9 * len(sel) >= n else 1)
+            for i in (0, 8):
+                w_ids, w_d = O.topk_exact(rows[sel], ids[sel], queries[i], 40, exhaustive=True)
+                assert np.array_equal(w[0][i], w_ids) and np.array_equal(w[1][i].view(np.uint64), w_d.view(np.uint64))
+        # a filter handle resolved once serves batches through the same pass
+        with ix.make_filter(ids[sel]) as f:
+            c = ix.search_filtered(queries[:9], K, f)
+            assert ix.stats()["last_path"] == 2
+            assert np.array_equal(c[0], b[0]) and np.array_equal(c[1].view(np.uint64), b[1].view(np.uint64))
+        # fewer eligible regular rows than k in reach of the coarse pass: the exact list path answers
+        few = np.concatenate([np.arange(5000, 5000 + 4096)])
+        g = ix.search_filtered(queries[:6], K, ids[few])
+        for i in range(6):
+            w_ids, w_d = O.topk_exact(rows[few], ids[few], queries[i], K, exhaustive=True)
+            assert np.array_equal(g[0][i], w_ids) and np.array_equal(g[1][i].view(np.uint64), w_d.view(np.uint64))
+
+
 def test_filter_handle_is_resolved_once_and_follows_upserts_and_deletes(Index, small_table):
     """`orx_filter_*`: same answers as the per-call filter; the device bitmap is rebuilt only when the id -> row
     map has changed, and then denotes the live rows whose id is in the set."""
@@ -730,9 +790,44 @@ def test_filter_handle_is_resolved_once_and_follows_upserts_and_deletes(Index, s
             ix.search_filtered(Q[:1], K, big)
 
 
+@pytest.mark.parametrize("dtype", ["fp32", "bf16"])
+def test_wide_k_batches_on_the_tensor_path(Index, synth100k, dtype):
+    """16 < k <= 64 with a batch: one tcgen05 pass whose per-(query, CTA) candidate lists hold 160 keys (k <= 16: 64) --
+    a list has to hold the rows within the coarse margin below its k-th entry too.  ids and distance bits equal the
+    oracle's for one query tile (single CTAs) and for CTA pairs; k > 64 keeps the exact fp32 scan."""
+    n = 30_000
+    X = synth100k.table(n)
+    Q, _ = synth100k.queries(200, n)
+    ids = _ids(n)
+    rows = X if dtype == "fp32" else stored_bf16_rows(X)
+    with Index(dtype, capacity=n) as ix:
+        ix.upsert(ids, X)
+        for k, nq, path in ((16, 9, 2), (17, 7, 2), (32, 200, 2), (33, 130, 2), (64, 200, 2), (64, 3, 2), (65, 3, 1), (128, 5, 1)):
+            g_ids, g_d, g_c = ix.search(Q[:nq], k)
+            assert ix.stats()["last_path"] == path, (k, nq)
+            for i in range(0, nq, 1 if nq < 10 else 9):
+                w_ids, w_d = O.topk_exact(rows, ids, Q[i], k)
+                assert g_c[i] == k and np.array_equal(g_ids[i], w_ids), (k, nq, i)
+                assert np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64)), (k, nq, i)
+        assert ix.stats()["fallback_exhaustive"] == 0
+    with Index(dtype) as ix:                                        # fewer live rows than k
+        ix.upsert(ids[:4200], X[:4200])
+        ix.delete(ids[100:4190])
+        g_ids, g_d, g_c = ix.search(Q[:4], 64)
+        keep = np.r_[0:100, 4190:4200]
+        for i in range(4):
+            w_ids, w_d = O.topk_exact(rows[keep], ids[keep], Q[i], 64)
+            assert g_c[i] == 64 and np.array_equal(g_ids[i], w_ids) and np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64))
+        g_ids, g_d, g_c = ix.search(Q[:4], 128)
+        for i in range(4):
+            w_ids, w_d = O.topk_exact(rows[keep], ids[keep], Q[i], 128)
+            assert g_c[i] == 110 and np.array_equal(g_ids[i, :110], w_ids) and np.isnan(g_d[i, 110:]).all()
+
+
 def test_large_k_for_a_wider_reranker_feed(Index, small_table):
-    """k up to 128 (SURVEY.md 8f-4): batches stay exact (fp32 scan per query), ties and short tables too;
-    the sharded exchange chunks the batch so that a slot still fits."""
+    """k up to 128: batches stay exact (k <= 64: tcgen05 scan with wider candidate lists, a tie wider than
+    a list falls back to the fp32 scan; beyond: fp32 scan per query), ties and short tables too; the sharded exchange
+    chunks the batch so that a slot still fits."""
     X, Q, _ = small_table
     n = 6000
     Xd = X[:n].copy()
@@ -741,7 +836,11 @@ def test_large_k_for_a_wider_reranker_feed(Index, small_table):
     with Index("fp32") as ix:
         ix.upsert(ids, Xd)
         _check_exact(ix, Xd, ids, np.concatenate([Q[:5], Xd[5:6]]), k=100)
-        assert ix.stats()["last_path"] == 1
+        assert ix.stats()["last_path"] == 1                    # k > 64: one fp32 scan per query
+        _check_exact(ix, Xd, ids, np.concatenate([Q[:5], Xd[5:6]]), k=60)
+        assert ix.stats()["last_path"] == 2                    # k <= 64: tcgen05 scan with 160-key candidate lists
+        st = ix.stats()
+        assert st["fallback_gemv"] + st["fallback_exhaustive"] >= 1     # the 161-row tie floods a list: exact re-answer
         ix.shard_connect([ix.shard_export(1, 0)])
         a = ix.search(Q[:9], 128)
         b = ix.search_sharded(Q[:9], 128)

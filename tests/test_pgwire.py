@@ -355,6 +355,59 @@ def test_pgcopy_load_rejects_a_nan_batch_and_keeps_earlier_batches():
 
 
 @pytest.mark.gpu
+def test_parallel_copy_streams_load_one_index_while_it_is_searched():
+    """Cold start over several connections (each COPY selects a slice of the ids): one loader per thread, each with its
+    own staging buffers and stream, all committing into ONE index; a reader thread searches meanwhile.  The table ends up
+    with exactly the rows of all streams and answers like the oracle."""
+    import threading
+    per, n_streams = 16384 * 2 + 77, 3                              # every loader flushes three device batches
+    parts = [_rows(per, seed=10 + i) for i in range(n_streams)]
+    for i, (ids_i, _) in enumerate(parts):
+        ids_i[:, 1] += np.uint64(i * 1_000_000)                     # disjoint id ranges
+    streams = [W.copy_binary_stream(ids_i, X_i) for ids_i, X_i in parts]
+    errors, results = [], [None] * n_streams
+    with orx.Index("fp32") as ix:
+        def load(i):
+            try:
+                with ix.pgcopy_loader() as ld:
+                    _feed_all(ld, streams[i], 1_000_003 + 17 * i)
+                results[i] = ld.result
+            except Exception as e:      # noqa: BLE001
+                errors.append(e)
+
+        stop = threading.Event()
+
+        def read():
+            try:
+                while not stop.is_set():
+                    if len(ix):
+                        got = ix.search(parts[0][1][:3], 4)
+                        assert (got[2] >= 1).all()
+            except Exception as e:      # noqa: BLE001
+                errors.append(e)
+
+        th = [threading.Thread(target=load, args=(i,)) for i in range(n_streams)] + [threading.Thread(target=read)]
+        for t in th:
+            t.start()
+        for t in th[:-1]:
+            t.join()
+        stop.set()
+        th[-1].join()
+        assert not errors, errors
+        assert results == [(per, 0)] * n_streams and len(ix) == per * n_streams
+        all_ids = np.concatenate([p[0] for p in parts])
+        all_X = np.concatenate([p[1] for p in parts])
+        probe = np.array([0, per - 1, per, 2 * per + 5, 3 * per - 1])
+        got, found = ix.fetch(all_ids[probe])
+        assert found.all() and np.array_equal(got.view(np.uint32), all_X[probe].view(np.uint32))
+        Q = all_X[[5, per + 9]] + np.float32(0.01)
+        g_ids, g_d, g_c = ix.search(Q, 12)
+        for i in range(2):
+            w_ids, w_d = O.topk_exact(all_X, all_ids, Q[i], 12)
+            assert np.array_equal(g_ids[i], w_ids) and np.array_equal(g_d[i].view(np.uint64), w_d.view(np.uint64))
+
+
+@pytest.mark.gpu
 def test_sharded_pgcopy_load_partitions_the_stream_without_loss():
     from outline_rag_b200.sharded import shard_of
     n = 900
