@@ -736,11 +736,14 @@ int resolve_unproven(orx_index *ix, const float *q_src, int nq, int k, const orx
     cudaStream_t st = ix->stream;
     // level 1: coarse tensor-core pass unproven -> exact fp32 scan for those queries
     if (path == 2) {
-        for (int j = 0; j < nq; ++j) {
-            if (!(hflags[j] & 1)) continue;
-            ix->stats.fallback_gemv += 1;
-            int rc = gemv_pass(ix, q_src, j, 1, k, ctx);
+        for (int j = 0; j < nq;) {
+            if (!(hflags[j] & 1)) { ++j; continue; }
+            int j1 = j + 1;                                    // a run of flagged neighbours shares its table passes
+            while (j1 < nq && (hflags[j1] & 1)) ++j1;
+            ix->stats.fallback_gemv += (uint64_t)(j1 - j);
+            int rc = gemv_pass(ix, q_src, j, j1 - j, k, ctx);
             if (rc != ORX_OK) return rc;
+            j = j1;
         }
         if (!host_readable) CK(cudaMemcpyAsync(hflags, flags, nq * sizeof(int), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

@@ -841,6 +841,9 @@ def test_large_k_for_a_wider_reranker_feed(Index, small_table):
         assert ix.stats()["last_path"] == 2                    # k <= 64: tcgen05 scan with 160-key candidate lists
         st = ix.stats()
         assert st["fallback_gemv"] + st["fallback_exhaustive"] >= 1     # the 161-row tie floods a list: exact re-answer
+        # neighbouring flagged queries are re-answered together (one batched fp32 pass for the run)
+        _check_exact(ix, Xd, ids, np.concatenate([Xd[5:6], Xd[5:6] * np.float32(2), Xd[100:101], Q[:2]]), k=60)
+        assert ix.stats()["fallback_gemv"] >= st["fallback_gemv"] + 3
         ix.shard_connect([ix.shard_export(1, 0)])
         a = ix.search(Q[:9], 128)
         b = ix.search_sharded(Q[:9], 128)

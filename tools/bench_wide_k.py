@@ -21,7 +21,12 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--verify", type=int, default=2, help="queries per call checked against a full oracle pass")
+    ap.add_argument("--ks", default="12,32,33,64,100,128")
+    ap.add_argument("--lib", default=None, help="A/B: load this build of liborx.so instead of the in-tree default")
     a = ap.parse_args()
+    if a.lib:
+        import types
+        sys.modules["orx_lib_override"] = types.SimpleNamespace(LIB_PATH=os.path.abspath(a.lib))
     import outline_rag_b200 as orx
     from bench import build_table
     from oracle import cosine_topk as O
@@ -36,7 +41,7 @@ def main():
         if a.verify:
             ix.export_rows(0, a.rows, ids, rows)
             X = rows.view(np.float32) if a.dtype == "fp32" else O.StreamingTopK.bf16_bits_to_f32(rows.view(np.uint16))
-        for k in (12, 32, 33, 64, 100, 128):
+        for k in [int(v) for v in a.ks.split(",")]:
             ms = []
             for it in range(a.iters + 2):
                 t0 = time.perf_counter()
@@ -54,7 +59,7 @@ def main():
                 t0 = time.perf_counter()
                 ix.search(Q[:1], k)
                 one.append((time.perf_counter() - t0) * 1e3)
-            print(json.dumps({"rows": a.rows, "dtype": a.dtype, "batch": a.batch, "k": k,
+            print(json.dumps({"rows": a.rows, "dtype": a.dtype, "batch": a.batch, "k": k, "lib": a.lib or "in-tree",
                               "call_wall_ms": float(np.median(ms)), "last_scan_ms": st["last_scan_ms"],
                               "path": "tcgen05" if st["last_path"] == 2 else "gemv per query",
                               "single_query_call_ms": float(np.median(one)),
