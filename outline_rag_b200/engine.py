@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import uuid
+import weakref
 from typing import Iterable, Sequence
 
 import numpy as np
@@ -140,6 +141,14 @@ class PgCopyLoader:
         self.result = None           # (rows_loaded, rows_null) once closed
         check(lib.orx_pgcopy_open_sharded(index._h if index is not None else None, int(world), int(rank),
                                           C.byref(self._ld)))
+        if index is not None:
+            index._loaders.add(self)     # Index.close() settles the batch this loader may have in flight first
+
+    def _abandon(self) -> None:
+        """The index is being closed under an open loader: wait for its batch in flight, free it, load nothing more."""
+        if self._ld:
+            ld, self._ld = self._ld, C.c_void_p()
+            lib.orx_pgcopy_close(ld, None, None)
 
     def feed(self, data) -> None:
         if not self._ld:
@@ -195,6 +204,7 @@ class Index:
         (`orx_create_multi`; rows placed by ``mix64(id) mod len(devices)``; searches run on all GPUs at once and the
         k candidates per query meet on ``devices[0]`` over NVLink).  Same methods as a single-GPU index."""
         self._h = C.c_void_p()
+        self._loaders = weakref.WeakSet()        # open COPY loaders (engine.PgCopyLoader)
         if devices is not None:
             devs = [int(d) for d in devices]
             if not devs:
@@ -214,6 +224,8 @@ class Index:
     # -- lifetime
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h:
+            for ld in list(getattr(self, "_loaders", ())):     # a COPY loader commits its batches on a helper thread
+                ld._abandon()
             lib.orx_destroy(self._h)
             self._h = C.c_void_p()
 

@@ -408,6 +408,22 @@ def test_parallel_copy_streams_load_one_index_while_it_is_searched():
 
 
 @pytest.mark.gpu
+def test_closing_the_index_under_an_open_loader_settles_its_batch_in_flight():
+    """The loader commits full batches on a helper thread: `Index.close()` waits for that batch and frees the loader
+    before the table goes away; the abandoned loader then refuses further input."""
+    n = 16384 + 50                                                  # one full batch is handed to the helper thread
+    ids, X = _rows(n, seed=4)
+    stream = W.copy_binary_stream(ids, X)
+    ix = orx.Index("fp32")
+    ld = ix.pgcopy_loader()
+    ld.feed(stream)
+    ix.close()
+    with pytest.raises(orx.OrxValueError, match="closed"):
+        ld.feed(b"x")
+    assert ld.close() == (0, 0)
+
+
+@pytest.mark.gpu
 def test_sharded_pgcopy_load_partitions_the_stream_without_loss():
     from outline_rag_b200.sharded import shard_of
     n = 900
