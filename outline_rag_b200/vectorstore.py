@@ -368,8 +368,9 @@ class GpuVectorStore(_VectorStoreBase):
         return [self._hydrate(ids[i], dist[i], int(cnt[i])) for i in range(ids.shape[0])]
 
     async def asimilarity_search_with_score_by_vector(self, embedding, k: int = 4, filter=None, **kw: Any):
-        if self.batcher is not None and filter is None:
-            ids, dist = await self.batcher.search(embedding, k)      # coalesced with concurrent requests
+        if self.batcher is not None and (filter is None or isinstance(filter, Filter)):
+            # coalesced with concurrent requests (those carrying the same prepared filter share one filtered pass)
+            ids, dist = await self.batcher.search(embedding, k, filter)
             return await asyncio.to_thread(self._hydrate, ids, dist, len(dist))
         return await asyncio.to_thread(self.similarity_search_with_score_by_vector, embedding, k, filter)
 

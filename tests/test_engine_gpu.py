@@ -714,7 +714,9 @@ def test_filtered_batches_take_one_tensor_core_pass(Index, synth100k, dtype):
                 qs = queries[-nq:]
                 g_ids, g_d, g_c = ix.search_filtered(qs, K, ids[rng.permutation(sel)])
                 assert ix.stats()["last_path"] == 2, (m, nq)
-                for i in range(nq):
+                # the three special queries at the end always; of a long batch otherwise every 6th (the oracle's
+                # exhaustive pass is what takes the time here)
+                for i in sorted(set(range(0, nq, 1 if nq < 20 else 6)) | set(range(nq - 3, nq))):
                     w_ids, w_d = O.topk_exact(rows[sel], ids[sel], qs[i], K, exhaustive=True)
                     assert g_c[i] == K
                     assert np.array_equal(g_ids[i], w_ids), (m, nq, i)
