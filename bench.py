@@ -691,6 +691,10 @@ def run_ours(a):
         extra(sh, owned, a.rows, "fp32", 64, 30, verify_n=4)
         recall_ref = step_out_to_host(sh.search(Qr, K))[0][:, :, 1].copy()        # fp32 answers for recall@12
         if world == 1:
+            # ---- SURVEY.md 8f-4 (the rows marked "next"): a wide-k batch and a filtered batch on the same table
+            for r in next_rows_on(sh.local, a.rows, "fp32"):
+                r["run"] = {"rows_per_gpu": owned, "parallelism": "row-shard x1", "exchange": "none"}
+                extras.append(r)
             # ---- BASELINE.json configs[4]: the refresh writer interleaved with single-query searches (mutates the table)
             r = mixed_on(sh.local, a.rows, "fp32", 6)
             r["run"] = {"rows_per_gpu": owned, "parallelism": "row-shard x1", "exchange": "none"}
@@ -788,6 +792,63 @@ def run_ours(a):
         cb.pop("_lat_measured", None)
         line["cpu_baseline"] = cb
     emit(line)
+
+
+def next_rows_on(ix, rows, dtype):
+    """SURVEY.md 8f-4 on the resident table, through the C-ABI with host buffers (wall clock per call): a batch of 64
+    queries with k = 64 (the wider reranker feed; tcgen05 scan with 160-key candidate lists) and a batch of 64 queries under
+    one prepared filter that admits every second row (one tcgen05 pass with the predicate folded into the row scale).
+    Each batch answer is compared, ids and distance bits, with the same query run alone through the single-query scan
+    (fp32 GEMV / bitmap GEMV): two independent device paths that must agree exactly."""
+    from orx_testkit.synth import Synth, default_centres
+    Qh, _ = Synth(default_centres(rows)).queries(64, rows)
+    out = []
+
+    def timed(fn, iters=10):
+        ms = []
+        for it in range(iters + 2):
+            t0 = time.perf_counter()
+            r = fn()
+            if it >= 2:
+                ms.append((time.perf_counter() - t0) * 1e3)
+        return r, float(np.median(ms))
+
+    def same(batch, single, i):
+        return bool(np.array_equal(batch[0][i], single[0][0]) and
+                    np.array_equal(batch[1][i].view(np.uint64), single[1][0].view(np.uint64)))
+
+    def entry(what, k, extra_cfg, r, ms, s0, s1, ok):
+        return {"config": dict({"workload": f"{what}, {rows}x{DIM} {dtype}", "rows": rows, "dim": DIM, "k": k, "batch": 64,
+                                "table_dtype": dtype}, **extra_cfg),
+                "value": 64 / ms * 1e3, "unit": UNIT, "steps": 10, "ms_per_step": ms,
+                "path": "tcgen05" if s1["last_path"] == 2 else "gemv",
+                "fallbacks": {"gemv": int(s1["fallback_gemv"] - s0["fallback_gemv"]),
+                              "exhaustive": int(s1["fallback_exhaustive"] - s0["fallback_exhaustive"])},
+                "h2d_bytes_per_step": 64 * DIM * 4, "d2h_bytes_per_step": 64 * (k * 24 + 4),
+                "verify": {"batch_equals_single_query_scan_ids_and_distance_bits": ok, "queries_checked": 3}}
+
+    s0 = ix.stats()
+    r, ms = timed(lambda: ix.search(Qh, 64))
+    s1 = ix.stats()
+    ok = all(same(r, ix.search(Qh[i:i + 1], 64), i) for i in (0, 31, 63))
+    out.append(entry("batch of 64 queries, k = 64", 64, {}, r, ms, s0, s1, ok))
+
+    allow = np.zeros((rows // 2, 2), np.uint64)
+    allow[:, 1] = np.arange(0, rows, 2, dtype=np.uint64)[:rows // 2]
+    t0 = time.perf_counter()
+    with ix.make_filter(allow) as flt:
+        prepare_ms = (time.perf_counter() - t0) * 1e3
+        s0 = ix.stats()
+        r, ms = timed(lambda: ix.search_filtered(Qh, K, flt))
+        s1 = ix.stats()
+        ok = all(same(r, ix.search_filtered(Qh[i:i + 1], K, flt), i) for i in (0, 31, 63))
+        single, single_ms = timed(lambda: ix.search_filtered(Qh[:1], K, flt), 5)
+    e = entry("batch of 64 queries under one prepared filter (every second row eligible)", K,
+              {"eligible_rows": rows // 2}, r, ms, s0, s1, ok)
+    e["filter_prepare_ms"] = prepare_ms
+    e["single_filtered_query_ms"] = single_ms
+    out.append(e)
+    return out
 
 
 def mixed_on(ix, rows, dtype, rounds):
