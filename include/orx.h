@@ -231,8 +231,12 @@ int orx_import_rows(orx_index *idx, const orx_id *ids, const void *rows_raw, uin
  * 16-byte uuid, dim == 1024 (ORX_ERR_DIM), unused == 0, NaN / infinite element (ORX_ERR_NONFINITE; the
  * batch holding it is rejected).  Rows whose embedding is NULL (the column is nullable) are skipped and
  * counted.  An id seen before -- in the table or earlier in the stream -- is replaced (upsert).
- * After an error every later feed fails; batches flushed before it stay loaded.  orx_pgcopy_close flushes
- * the tail, reports the totals and frees the loader, also after an error (its return code repeats it).
+ * A full batch is copied, decoded and committed by a helper thread of the loader while the caller feeds
+ * the next one (two staging buffer sets, the loader's own stream), so the error of a batch is reported by
+ * the NEXT feed or by orx_pgcopy_close.  After an error every later feed fails; batches flushed before it
+ * stay loaded.  orx_pgcopy_close flushes the tail, waits for the batch in flight, reports the totals and
+ * frees the loader, also after an error (its return code repeats it).  Several loaders may feed one index
+ * concurrently (one thread each); a loader must be closed before its index is destroyed.
  * idx == NULL opens a DRY RUN: framing and element checks on the host, nothing loaded, no GPU needed. */
 typedef struct orx_pgcopy orx_pgcopy;
 int orx_pgcopy_open(orx_index *idx, orx_pgcopy **out);
