@@ -67,6 +67,8 @@ class IndexServer:
         self.batcher = QueryBatcher(index, max_batch, batch_window_ms) if batch_window_ms is not None else None
         self._server: Optional[asyncio.AbstractServer] = None
         self._write_lock = asyncio.Lock()
+        self._filters: dict[int, object] = {}        # prepared filters (device-resident in this process) by id
+        self._next_fid = 0
 
     async def start(self) -> None:
         if os.path.exists(self.path):
@@ -103,6 +105,19 @@ class IndexServer:
         finally:
             writer.close()
 
+    @staticmethod
+    def _pack_rows(res, k: int) -> dict:
+        """Per-query results of the batcher -> the padded arrays of `Index.search`; the first failure is raised."""
+        for r in res:
+            if isinstance(r, Exception):
+                raise r
+        ids = np.zeros((len(res), k, 2), np.uint64)
+        dist = np.full((len(res), k), np.nan)
+        cnt = np.zeros(len(res), np.int32)
+        for i, (a, b) in enumerate(res):
+            ids[i, :len(b)], dist[i, :len(b)], cnt[i] = a, b, len(b)
+        return {"ids": _pack_arr(ids), "dist": _pack_arr(dist), "cnt": _pack_arr(cnt)}
+
     async def _handle(self, req: dict) -> dict:
         try:
             op = req.get("op")
@@ -111,21 +126,33 @@ class IndexServer:
                 k = int(req["k"])
                 if self.batcher is not None:
                     res = await asyncio.gather(*[self.batcher.search(q, k) for q in Q], return_exceptions=True)
-                    for r in res:
-                        if isinstance(r, Exception):
-                            raise r
-                    ids = np.zeros((len(res), k, 2), np.uint64)
-                    dist = np.full((len(res), k), np.nan)
-                    cnt = np.zeros(len(res), np.int32)
-                    for i, (a, b) in enumerate(res):
-                        ids[i, :len(b)], dist[i, :len(b)], cnt[i] = a, b, len(b)
-                else:
-                    ids, dist, cnt = await asyncio.to_thread(self.index.search, Q, k)
+                    return self._pack_rows(res, k)
+                ids, dist, cnt = await asyncio.to_thread(self.index.search, Q, k)
                 return {"ids": _pack_arr(ids), "dist": _pack_arr(dist), "cnt": _pack_arr(cnt)}
             if op == "search_filtered":
-                ids, dist, cnt = await asyncio.to_thread(self.index.search_filtered, _unpack_arr(req["q"]), int(req["k"]),
-                                                         _unpack_arr(req["allow"]))
+                Q, k = _unpack_arr(req["q"]), int(req["k"])
+                if "fid" in req:
+                    flt = self._filters.get(int(req["fid"]))
+                    if flt is None:
+                        return {"err": ORX_ERR_INVALID, "msg": f"unknown filter {req['fid']}", "value_error": True}
+                    if self.batcher is not None:
+                        # searches under the same prepared filter, from any worker, share one filtered pass
+                        res = await asyncio.gather(*[self.batcher.search(q, k, flt) for q in Q], return_exceptions=True)
+                        return self._pack_rows(res, k)
+                    ids, dist, cnt = await asyncio.to_thread(self.index.search_filtered, Q, k, flt)
+                else:
+                    ids, dist, cnt = await asyncio.to_thread(self.index.search_filtered, Q, k, _unpack_arr(req["allow"]))
                 return {"ids": _pack_arr(ids), "dist": _pack_arr(dist), "cnt": _pack_arr(cnt)}
+            if op == "filter_create":
+                flt = await asyncio.to_thread(self.index.make_filter, _unpack_arr(req["allow"]))
+                self._next_fid += 1
+                self._filters[self._next_fid] = flt
+                return {"fid": self._next_fid}
+            if op == "filter_drop":
+                flt = self._filters.pop(int(req["fid"]), None)
+                if flt is not None and hasattr(flt, "close"):
+                    await asyncio.to_thread(flt.close)
+                return {"ok": True}
             if op == "upsert":
                 async with self._write_lock:
                     await asyncio.to_thread(self.index.upsert, _unpack_arr(req["ids"]), _unpack_arr(req["vecs"]))
@@ -198,6 +225,29 @@ class _Conn:
         return bytes(buf)
 
 
+class RemoteFilter:
+    """A prepared filter that lives in the owner process (`engine.Filter` there); the worker holds its number."""
+
+    is_filter_handle = True
+
+    def __init__(self, index: "RemoteIndex", fid: int):
+        self._index, self._fid = index, fid
+
+    def close(self) -> None:
+        fid, self._fid = self._fid, None
+        if fid is not None:
+            try:
+                self._index._call({"op": "filter_drop", "fid": fid})
+            except OrxError:
+                pass                      # the owner is gone: so is the filter
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 class RemoteIndex:
     """`Index`-shaped proxy used by a worker process: blocking calls over a pool of unix-socket connections
     (thread-safe; `GpuVectorStore` already runs index calls in `asyncio.to_thread`)."""
@@ -264,14 +314,26 @@ class RemoteIndex:
         return _unpack_arr(r["ids"]), _unpack_arr(r["dist"]), _unpack_arr(r["cnt"])
 
     def search_filtered(self, queries, k: int, allow_ids):
-        """`Index.search_filtered` on the owner (ids are resolved there on every call; device-resident
-        `Filter` handles live in the owner process and do not cross the socket)."""
+        """`Index.search_filtered` on the owner: with ids (resolved there on every call) or with a `RemoteFilter`
+        (`make_filter`: resolved once, device-resident in the owner process; only its number crosses the socket)."""
         from .engine import ids_to_array
         q = np.asarray(queries, dtype=np.float32)
         if q.ndim == 1:
             q = q.reshape(1, -1)
-        r = self._call({"op": "search_filtered", "q": _pack_arr(q), "k": int(k), "allow": _pack_arr(ids_to_array(allow_ids))})
+        req = {"op": "search_filtered", "q": _pack_arr(q), "k": int(k)}
+        if isinstance(allow_ids, RemoteFilter):
+            if allow_ids._index is not self or allow_ids._fid is None:
+                raise OrxValueError(ORX_ERR_INVALID, "filter is closed or belongs to another index")
+            req["fid"] = allow_ids._fid
+        else:
+            req["allow"] = _pack_arr(ids_to_array(allow_ids))
+        r = self._call(req)
         return _unpack_arr(r["ids"]), _unpack_arr(r["dist"]), _unpack_arr(r["cnt"])
+
+    def make_filter(self, allow_ids) -> "RemoteFilter":
+        from .engine import ids_to_array
+        fid = int(self._call({"op": "filter_create", "allow": _pack_arr(ids_to_array(allow_ids))})["fid"])
+        return RemoteFilter(self, fid)
 
     def upsert(self, ids, vecs) -> None:
         from .engine import ids_to_array
@@ -282,4 +344,4 @@ class RemoteIndex:
         return int(self._call({"op": "delete", "ids": _pack_arr(ids_to_array(ids))})["removed"])
 
 
-__all__ = ["IndexServer", "RemoteIndex", "ServerThread", "serve_in_thread"]
+__all__ = ["IndexServer", "RemoteFilter", "RemoteIndex", "ServerThread", "serve_in_thread"]

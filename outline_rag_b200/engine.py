@@ -102,6 +102,8 @@ class Filter:
     """A reusable predicate on chunk ids (`orx_filter_*`): the id -> row resolution and the row bitmap stay
     on the device between searches and follow upserts / deletes.  Pass it to `Index.search_filtered`."""
 
+    is_filter_handle = True       # what `GpuVectorStore` / `QueryBatcher` look for (daemon.RemoteFilter has it too)
+
     def __init__(self, index: "Index", allow_ids):
         self._f = C.c_void_p()
         self._index = index

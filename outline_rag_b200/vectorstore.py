@@ -30,6 +30,11 @@ from ._lib import ORX_DIM, ORX_ERR_DIM, ORX_ERR_NONFINITE, OrxValueError
 from .batcher import QueryBatcher
 from .engine import Filter, Index, ids_to_array, ids_to_uuid_strs
 
+
+def _is_handle(flt) -> bool:
+    """A prepared filter (engine.Filter, daemon.RemoteFilter) rather than a metadata predicate."""
+    return bool(getattr(flt, "is_filter_handle", False))
+
 # The reference's seam is typed: `rag.vector_store: AsyncPGVectorStore` (a langchain VectorStore), its
 # `.as_retriever(...)` result is handed to the pydantic-validated `ContextualCompressionRetriever(base_retriever=...)`
 # (reference app/rag.py:28-31, :85-99).  So when the host application has langchain-core, GpuVectorStore IS a
@@ -350,14 +355,15 @@ class GpuVectorStore(_VectorStoreBase):
             # the metadata predicate is resolved where the metadata lives (doc store / Postgres), the
             # similarity ordering of the eligible chunks runs on the GPU (orx_search_filtered); a prepared
             # filter (`prepare_filter`) skips both the look-up and the id -> row resolution
-            allow = filter if isinstance(filter, Filter) else self.doc_store.ids_for_filter(filter)
+            allow = filter if _is_handle(filter) else self.doc_store.ids_for_filter(filter)
             ids, dist, cnt = self.index.search_filtered(q, k, allow)
         else:
             ids, dist, cnt = self.index.search(q, k)
         return self._hydrate(ids[0], dist[0], int(cnt[0]))
 
-    def prepare_filter(self, filter: dict) -> Filter:
-        """Resolve a metadata predicate ONCE into a device-resident `Filter` that can be passed as `filter=`
+    def prepare_filter(self, filter: dict):
+        """Resolve a metadata predicate ONCE into a device-resident `Filter` (a `RemoteFilter` when the index is a
+        `daemon.RemoteIndex`: the handle then lives in the owner process) that can be passed as `filter=`
         to every later search (a collection- or source-scoped assistant asks the same predicate each time).
         It denotes the chunk ids matching NOW; chunks added later need a new `prepare_filter`."""
         return self.index.make_filter(self.doc_store.ids_for_filter(filter))
@@ -368,7 +374,7 @@ class GpuVectorStore(_VectorStoreBase):
         return [self._hydrate(ids[i], dist[i], int(cnt[i])) for i in range(ids.shape[0])]
 
     async def asimilarity_search_with_score_by_vector(self, embedding, k: int = 4, filter=None, **kw: Any):
-        if self.batcher is not None and (filter is None or isinstance(filter, Filter)):
+        if self.batcher is not None and (filter is None or _is_handle(filter)):
             # coalesced with concurrent requests (those carrying the same prepared filter share one filtered pass)
             ids, dist = await self.batcher.search(embedding, k, filter)
             return await asyncio.to_thread(self._hydrate, ids, dist, len(dist))

@@ -177,3 +177,86 @@ def test_real_index_served_to_another_process(small_table, tmp_path):
         w_ids, w_d = O.topk_exact(X, ids, Q[i], 12)
         assert got_ids[i] == O.ids_to_ints(w_ids)
     assert dist0 == [float(d).hex() for d in O.topk_exact(X, ids, Q[0], 12)[1]]
+
+
+def test_prepared_filters_live_in_the_owner_and_their_searches_are_coalesced(small_table, tmp_path):
+    """`RemoteIndex.make_filter`: the allow-list crosses the socket once, the handle stays in the owner process, and
+    searches of different workers under the same handle share one filtered pass of the owner's batcher.  A
+    `GpuVectorStore` over a `RemoteIndex` prepares and uses such a filter like a local one."""
+    import asyncio
+    import outline_rag_b200 as orx
+    from outline_rag_b200.daemon import RemoteFilter, RemoteIndex, serve_in_thread
+    X, Q, _ = small_table
+    ids = O.ids_arange(0, 500)
+
+    class Handle:                                               # what FakeOwner.make_filter hands out
+        def __init__(self, allow):
+            self.allow, self.closed = np.asarray(allow, np.uint64).reshape(-1, 2), False
+
+        def close(self):
+            self.closed = True
+
+    class Owner(FakeOwner):
+        def __init__(self, *a):
+            super().__init__(*a)
+            self.handles = []
+
+        def make_filter(self, allow):
+            self.handles.append(Handle(allow))
+            return self.handles[-1]
+
+        def search_filtered(self, Q, k, allow):
+            if isinstance(allow, Handle):
+                self.log.append(("search_with_handle", int(np.asarray(Q).shape[0])))
+                allow = allow.allow
+            return super().search_filtered(Q, k, allow)
+
+    owner = Owner(X[:500], ids)
+    path = str(tmp_path / "orx.sock")
+    srv = serve_in_thread(owner, path, batch_window_ms=40.0, max_batch=64)
+    try:
+        a, b = RemoteIndex(path), RemoteIndex(path)
+        flt = a.make_filter(ids[100:300])
+        assert isinstance(flt, RemoteFilter) and len(owner.handles) == 1 and len(owner.handles[0].allow) == 200
+        out = {}
+
+        def worker(name, client, qs):
+            out[name] = [client.search_filtered(Q[i], 7, flt if client is a else ids[100:300]) for i in qs]
+
+        t1 = threading.Thread(target=worker, args=("a1", a, [0, 1]))
+        t2 = threading.Thread(target=worker, args=("a2", a, [2, 3]))
+        t1.start(); t2.start(); t1.join(); t2.join()
+        for name, qs in (("a1", [0, 1]), ("a2", [2, 3])):
+            for (g_ids, g_d, g_c), qi in zip(out[name], qs):
+                w_ids, w_d = O.topk_exact(X[100:300], ids[100:300], Q[qi], 7)
+                assert g_c[0] == 7 and np.array_equal(g_ids[0], w_ids) and np.array_equal(g_d[0], w_d)
+        handle_calls = [n for op, n in owner.log if op == "search_with_handle"]
+        assert sum(handle_calls) == 4 and max(handle_calls) >= 2        # two threads' searches shared a filtered pass
+        with pytest.raises(orx.OrxValueError, match="another index"):
+            b.search_filtered(Q[0], 3, flt)
+
+        # the vector store of a worker process: prepare once, search under the handle
+        class Emb:
+            async def aembed_query(self, text):
+                return X[int(text)]
+
+        store = orx.GpuVectorStore(a, Emb(), batch_window_ms=None)
+        store.doc_store.put_many([str(uuid_of(i)) for i in range(500)], [str(i) for i in range(500)],
+                                 [{"source_id": f"d{i // 100}"} for i in range(500)])
+        prepared = store.prepare_filter({"source_id": "d2"})
+        assert isinstance(prepared, RemoteFilter)
+        hits = asyncio.run(store.asimilarity_search("250", k=3, filter=prepared))
+        assert [h.page_content for h in hits][0] == "250" and all(200 <= int(h.page_content) < 300 for h in hits)
+        prepared.close()
+        flt.close()
+        assert all(h.closed for h in owner.handles)
+        with pytest.raises(orx.OrxValueError, match="closed"):
+            a.search_filtered(Q[0], 3, flt)
+        a.close(); b.close()
+    finally:
+        srv.stop()
+
+
+def uuid_of(i):
+    import uuid
+    return uuid.UUID(int=i)
