@@ -260,3 +260,40 @@ def test_prepared_filters_live_in_the_owner_and_their_searches_are_coalesced(sma
 def uuid_of(i):
     import uuid
     return uuid.UUID(int=i)
+
+
+@pytest.mark.gpu
+def test_remote_prepared_filter_on_a_real_index(small_table, tmp_path):
+    """The same over a real device table: a worker prepares a filter that admits 5000 of 8192 rows (bitmap regime); 12
+    concurrent searches under it are coalesced by the owner into filtered tensor-core passes; answers equal the oracle's."""
+    import outline_rag_b200 as orx
+    from outline_rag_b200.daemon import RemoteIndex, serve_in_thread
+    X, Q, _ = small_table
+    n = X.shape[0]
+    ids = O.ids_arange(0, n)
+    sel = np.sort(np.random.default_rng(8).choice(n, size=5000, replace=False))
+    path = str(tmp_path / "orx.sock")
+    with orx.Index("fp32") as ix:
+        ix.upsert(ids, X)
+        srv = serve_in_thread(ix, path, batch_window_ms=30.0, max_batch=64)
+        try:
+            client = RemoteIndex(path, max_connections=16)
+            with client.make_filter(ids[sel]) as flt:
+                out = [None] * 12
+
+                def one(i):
+                    out[i] = client.search_filtered(Q[i], 12, flt)
+
+                th = [threading.Thread(target=one, args=(i,)) for i in range(12)]
+                for t in th:
+                    t.start()
+                for t in th:
+                    t.join()
+                st = ix.stats()
+            client.close()
+        finally:
+            srv.stop()
+    for i in range(12):
+        w_ids, w_d = O.topk_exact(X[sel], ids[sel], Q[i], 12, exhaustive=True)
+        assert np.array_equal(out[i][0][0], w_ids) and np.array_equal(out[i][1][0].view(np.uint64), w_d.view(np.uint64)), i
+    assert st["searches"] < 12 and st["queries"] == 12 and st["last_path"] == 2      # coalesced, tensor-core pass
