@@ -42,7 +42,7 @@ def tables(draw):
     if wide:
         vals = [int(v) << 70 | int(rng.integers(0, 2**60)) for v in vals]
     ids = O.ids_from_ints([int(v) for v in vals])
-    k = draw(st.sampled_from([1, 5, 12, 16, 17, 32]))
+    k = draw(st.sampled_from([1, 5, 12, 16, 17, 32, 40, 64, 65, 128]))
     nq = draw(st.sampled_from([1, 2, 7, 33]))
     qsrc = draw(st.sampled_from(["rows", "random", "mixed"]))
     if qsrc == "rows":
@@ -55,7 +55,7 @@ def tables(draw):
     return X, ids, np.ascontiguousarray(Q), k, n_del, draw(st.sampled_from(["fp32", "bf16"]))
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@settings(max_examples=80, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
 @given(tables())
 def test_engine_equals_oracle_on_adversarial_tables(case):
     import outline_rag_b200 as orx
@@ -75,3 +75,37 @@ def test_engine_equals_oracle_on_adversarial_tables(case):
         assert g_c[i] == m
         assert np.array_equal(g_ids[i, :m], w_ids), (dtype, k, i)
         assert np.array_equal(g_d[i, :m].view(np.uint64), w_d.view(np.uint64)), (dtype, k, i)
+
+
+@settings(max_examples=60, deadline=None, suppress_health_check=list(HealthCheck), derandomize=True)
+@given(tables(), st.sampled_from([0.02, 0.5, 0.97]), st.integers(0, 2**31 - 1))
+def test_filtered_search_equals_oracle_on_adversarial_tables(case, frac, seed):
+    """The same tables under a random allow-list: the list regime (few eligible rows), the bitmap scan (single queries)
+    and the masked-scale tensor-core pass (batches) must all equal the oracle on the eligible subset."""
+    import outline_rag_b200 as orx
+    from tests._helpers import stored_bf16_rows
+    X, ids, Q, k, n_del, dtype = case
+    rows = X if dtype == "fp32" else stored_bf16_rows(X)
+    rng = np.random.default_rng(seed)
+    with orx.Index(dtype) as ix:
+        ix.upsert(ids, X)
+        keep = np.ones(X.shape[0], bool)
+        if n_del:
+            keep[:n_del] = False
+            ix.delete(ids[:n_del])
+        allowed = rng.random(X.shape[0]) < frac
+        allowed[rng.integers(0, X.shape[0])] = True
+        unknown = O.ids_from_ints([2**100 + 7, 2**100 + 8])              # ids the table has never seen are ignored
+        g_ids, g_d, g_c = ix.search_filtered(Q, k, np.concatenate([ids[allowed], unknown]))
+    sel = keep & allowed
+    for i in range(Q.shape[0]):
+        if not sel.any():
+            assert g_c[i] == 0
+            continue
+        w_ids, w_d = O.topk_exact(rows[sel], ids[sel], Q[i], k, exhaustive=True)
+        m = len(w_d)
+        assert g_c[i] == m
+        assert np.array_equal(g_ids[i, :m], w_ids), (dtype, k, i, frac)
+        nan = np.isnan(w_d)
+        assert np.array_equal(np.isnan(g_d[i, :m]), nan)
+        assert np.array_equal(g_d[i, :m][~nan].view(np.uint64), w_d[~nan].view(np.uint64)), (dtype, k, i, frac)
