@@ -119,13 +119,15 @@ struct orx_pgcopy {
     std::string job_err;
     uint64_t rows = 0, nulls = 0, foreign = 0, bytes = 0;
     int err = ORX_OK;
+    std::string err_text;
 };
 
 namespace {
 
-int pg_fail(orx_pgcopy *ld, int code) {
+int pg_fail(orx_pgcopy *ld, int code) {       // the caller has just recorded the message (orx::set_error)
     ld->state = orx_pgcopy::FAILED;
     ld->err = code;
+    ld->err_text = orx_last_error();           // kept: the close may come from another thread (asyncio.to_thread)
     return code;
 }
 
@@ -446,7 +448,15 @@ int orx_pgcopy_close(orx_pgcopy *ld, uint64_t *rows_loaded, uint64_t *rows_null)
     if (rows_null) *rows_null = 0;
     if (!ld) return orx::set_error(ORX_ERR_INVALID, "loader is null");
     int rc = ld->err;
-    if (ld->state != orx_pgcopy::FAILED) {
+    if (ld->state == orx_pgcopy::FAILED) {
+        // a batch may still be in flight (the failure was found while parsing behind it): it counts if it lands
+        if (ld->job_running) {
+            ld->job.join();
+            ld->job_running = false;
+            if (ld->job_rc == ORX_OK) ld->rows += ld->job_rows;
+        }
+        orx::set_error(rc, "%s", ld->err_text.c_str());
+    } else {
         rc = pg_drain(ld, true);
         if (rc == ORX_OK) rc = pg_join(ld);          // the last batch has landed (or failed)
         // EOF at a tuple boundary ends the data like the -1 marker does (Postgres' CopyFrom treats it so);

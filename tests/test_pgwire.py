@@ -282,6 +282,27 @@ def test_loader_fails_for_good_after_an_error():
     assert ld.close() == (0, 0)        # closing twice is harmless
 
 
+def test_close_repeats_the_loaders_own_error_even_from_another_thread():
+    """`aload_pgcopy` feeds and closes on worker threads (`asyncio.to_thread`): the error text is kept by the loader,
+    not in the feeding thread's last-error slot."""
+    import threading
+    ld = orx.PgCopyLoader(None)
+    with pytest.raises(orx.OrxValueError, match="signature not recognized"):
+        ld.feed(b"not a copy stream, but long enough")
+    seen = []
+
+    def close_elsewhere():
+        try:
+            ld.close()
+        except orx.OrxError as e:
+            seen.append(str(e))
+
+    t = threading.Thread(target=close_elsewhere)
+    t.start()
+    t.join()
+    assert len(seen) == 1 and "signature not recognized" in seen[0]
+
+
 # ------------------------------------------------------------------------------- GPU: the load itself
 @pytest.mark.gpu
 @pytest.mark.parametrize("dtype", ["fp32", "bf16"])
