@@ -178,3 +178,23 @@ def test_vectorstore_over_a_multi_gpu_index(synth100k):
 
     for devs in _device_sets():
         asyncio.run(main(devs))
+
+
+def test_group_cold_start_from_a_copy_stream(synth100k):
+    """COPY BINARY cold start into a multi-GPU index: the loader stages and decodes on the first device, the upsert
+    scatters the decoded rows to their shards; the table then answers like the oracle."""
+    import outline_rag_b200 as orx
+    from oracle import pgvector_wire as W
+    n = 16384 + 3000                                            # two device batches
+    X = synth100k.table(n)
+    ids = O.ids_arange(0, n)
+    stream = W.copy_binary_stream(ids, X)
+    Q, _ = synth100k.queries(5, n)
+    for devs in _device_sets():
+        with orx.Index("fp32", devices=devs) as ix:
+            with ix.pgcopy_loader() as ld:
+                for o in range(0, len(stream), 3_000_017):
+                    ld.feed(stream[o:o + 3_000_017])
+            assert ld.result == (n, 0) and len(ix) == n
+            _exact(ix, X, ids, Q[:1])
+            _exact(ix, X, ids, Q)
