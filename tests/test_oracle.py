@@ -272,3 +272,27 @@ def test_streaming_candidates_merge_across_shards(small_table):
         m_ids, m_d = O.merge_shards([s[j] for s in shards], K)
         w_ids, w_d = O.topk_exact(X, ids, Q[j], K)
         assert np.array_equal(m_ids, w_ids) and np.array_equal(m_d.view(np.uint64), w_d.view(np.uint64))
+
+
+def test_oracle_agrees_with_independent_third_party_implementations(small_table):
+    """No reference fixture exists, but two independent implementations of the same published definition do: SciPy's
+    `spatial.distance.cosine` and scikit-learn's brute-force cosine k-NN.  Distances agree to double rounding
+    (tolerance 1e-12 stated here: they sum in another order than the canonical tree) and the neighbour ids are identical
+    wherever the gap to the next distance exceeds that tolerance."""
+    from scipy.spatial.distance import cosine as scipy_cosine
+    from sklearn.neighbors import NearestNeighbors
+    X, Q, _ = small_table
+    X = X[:3000].astype(np.float64)
+    ids = _ids(3000)
+    nn = NearestNeighbors(n_neighbors=K + 1, metric="cosine", algorithm="brute").fit(X)
+    nd, ni = nn.kneighbors(Q[:16].astype(np.float64))
+    for i in range(16):
+        w_ids, w_d = O.topk_exact(X.astype(np.float32), ids, Q[i], K)
+        rows = [int(v) for v in O.ids_to_ints(w_ids)]
+        for r, d in zip(rows, w_d):
+            assert abs(scipy_cosine(X[r], Q[i].astype(np.float64)) - d) < 1e-12
+        assert np.allclose(nd[i, :K], w_d, rtol=0, atol=1e-12)
+        clear = np.diff(nd[i]) > 1e-10                           # positions whose successor is clearly farther
+        for p in range(K):
+            if clear[p] and (p == 0 or clear[p - 1]):
+                assert ni[i, p] == rows[p], (i, p)
