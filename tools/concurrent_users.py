@@ -23,6 +23,13 @@ class NoEmb:                                                     # queries arriv
     pass
 
 
+class AnyDocStore(orx.MemoryDocStore):
+    """Stands in for Postgres holding content + metadata of all 10M chunks: every id has a row."""
+
+    def get_many(self, ids):
+        return [("chunk " + i, {"source_id": "doc"}) for i in ids]
+
+
 async def scenario(store, Q, clients, rounds):
     lat = []
 
@@ -51,7 +58,7 @@ def main():
     build_table(ix.upsert, 0, a.rows, 0, 1)
     Q, _ = Synth(default_centres(a.rows)).queries(512, a.rows)
     for window in (None, 1.0):
-        store = orx.GpuVectorStore(ix, NoEmb(), batch_window_ms=window, max_batch=256)
+        store = orx.GpuVectorStore(ix, NoEmb(), doc_store=AnyDocStore(), batch_window_ms=window, max_batch=256)
         for c in a.clients:
             rounds = max(4, min(40, 1024 // c))
             asyncio.run(scenario(store, Q, min(c, 8), 2))                        # warm-up
